@@ -1,0 +1,149 @@
+/* mrhash_b200.h — C ABI of libmrhash_b200.so, the B200-native drop-in for mrhash's
+ * GeoWrapper::compute() hot path (depth-ray block allocation into the spatial hash, TSDF fusion,
+ * garbage collection, variance-adaptive re-allocation) plus extractMesh() and serializeData().
+ *
+ * The reference has no C ABI: its boundary is the nanobind class `pygeowrapper.GeoWrapper`
+ * (/root/reference/mrhash/src/sdf/pybind/pygeowrapper.cpp:12-84) over the C++ class
+ * pygeowrapper::GeoWrapper (/root/reference/mrhash/src/sdf/geowrapper.h:18-260). Every entry
+ * point below names the reference member it replaces; INTEGRATION.md shows the binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions: every call returns 0 on success, non-zero on failure with a message available from
+ * mrh_last_error() (thread-local). One handle = one CUDA device; a handle is not thread-safe
+ * (like the reference). compute() is asynchronous on the handle's stream; every call that returns
+ * data to the host synchronises first.
+ */
+#ifndef MRHASH_B200_H
+#define MRHASH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRH_ABI_VERSION 1
+
+typedef struct mrh_map mrh_map;
+
+/* Constructor arguments of GeoWrapper (pygeowrapper.cpp:14-29, geowrapper.cpp:9-81) plus explicit
+ * sizing. A sizing field left at 0 is derived from cudaMemGetInfo with the reference's ratios
+ * (params.h:33-37, geowrapper.cpp:37-54) in 64-bit arithmetic. */
+typedef struct {
+  float sdf_truncation;
+  float sdf_truncation_scale;
+  int32_t integration_weight_sample;
+  float virtual_voxel_size;
+  int32_t n_frames_invalidate_voxels;
+  int32_t voxel_extents_scale;
+  int32_t viewer_active; /* accepted, ignored: no viewer thread */
+  float marching_cubes_threshold;
+  int32_t min_weight_threshold;
+  float min_depth;
+  float max_depth;
+  float sdf_var_threshold;
+  float vertices_merging_threshold;
+  int32_t projective_sdf;
+  /* sizing (0 = auto) */
+  uint64_t num_sdf_blocks;
+  uint64_t hash_num_buckets;
+  uint64_t max_num_triangles;
+  /* placement */
+  int32_t device;      /* CUDA device ordinal, -1 = current */
+  int32_t shard_rank;  /* this handle owns hash buckets [rank*nb/world, (rank+1)*nb/world) */
+  int32_t shard_world; /* 0 or 1 = unsharded */
+  int32_t reserved;
+} mrh_params;
+
+/* per-run totals since creation / mrh_reset_stats (the work-unit accounting of BASELINE.md §4) */
+typedef struct {
+  uint64_t frames;
+  uint64_t rays_valid;
+  uint64_t blocks_new;     /* B_new */
+  uint64_t blocks_visible; /* B_vis summed over frames */
+  uint64_t voxels_updated; /* V_upd */
+  uint64_t blocks_freed;
+  uint64_t blocks_realloc;
+  uint64_t dropped_heap;   /* "mem size exceed, not inserting hash entry" events */
+  uint64_t dropped_table;
+  uint64_t live_blocks;    /* currently allocated */
+  int64_t heap_free;       /* getHeapHighFreeCount() (voxel_data_structures.cpp:148-153) */
+  int64_t heap_low_free;
+} mrh_stats;
+
+/* record format of mrh_dump_state (test / parity only) */
+typedef struct {
+  int32_t x, y, z, resolution, ptr;
+} mrh_dump_entry;
+
+const char* mrh_last_error(void);
+int mrh_abi_version(void);
+
+/* GeoWrapper::GeoWrapper / ~GeoWrapper (geowrapper.cpp:9-84) */
+int mrh_params_default(mrh_params* p);
+int mrh_create(const mrh_params* p, mrh_map** out);
+int mrh_destroy(mrh_map* m);
+
+/* GeoWrapper::setCamera (geowrapper.cpp:98-116); camera_model 0 = pinhole, 1 = spherical */
+int mrh_set_camera(mrh_map* m, float fx, float fy, float cx, float cy, int rows, int cols, float min_depth, float max_depth, int camera_model);
+/* GeoWrapper::setCurrPose (geowrapper.cpp:86-92): translation + quaternion (x, y, z, w) */
+int mrh_set_pose(mrh_map* m, const float translation[3], const float quaternion_xyzw[4]);
+/* same state, given directly as a row-major 4x4 cam_in_world (what compute() hands to Camera::setCamInWorld) */
+int mrh_set_pose_matrix(mrh_map* m, const float cam_in_world[16]);
+/* GeoWrapper::getCurrPose (geowrapper.h:94) */
+int mrh_get_pose_matrix(mrh_map* m, float out[16]);
+/* GeoWrapper::setCameraInLidar (geowrapper.cpp:94-96) */
+int mrh_set_camera_in_lidar(mrh_map* m, const float T[16]);
+
+/* GeoWrapper::setDepthImage (geowrapper.cpp:246-274): host float32 [rows, cols], copied */
+int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols);
+/* GeoWrapper::setRGBImage (geowrapper.cpp:276-298): host uint8 [rows, cols, 3], copied */
+int mrh_set_rgb(mrh_map* m, const uint8_t* rgb, int rows, int cols);
+/* same, for callers that hold float32 colour (apps/utils/depth_reader.py:83-93); cast to uint8 like nanobind's implicit conversion */
+int mrh_set_rgb_f32(mrh_map* m, const float* rgb, int rows, int cols);
+/* inputs already resident in device memory (no copy; the pointers must stay valid until the next compute() completes) */
+int mrh_set_depth_device(mrh_map* m, const float* d_depth, int rows, int cols);
+int mrh_set_rgb_device(mrh_map* m, const uint8_t* d_rgb, int rows, int cols);
+/* GeoWrapper::setPointCloud (geowrapper.cpp:345-405, 469-505): host float32 [n, 3]; normals may be NULL */
+int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* normals_or_null);
+
+/* GeoWrapper::compute (geowrapper.cpp:118-148) */
+int mrh_compute(mrh_map* m);
+/* wait for all queued work of this handle */
+int mrh_synchronize(mrh_map* m);
+
+/* GeoWrapper::streamAllOut (geowrapper.cpp:559-561) */
+int mrh_stream_all_out(mrh_map* m);
+/* GeoWrapper::extractMesh (geowrapper.cpp:150-230): marching cubes + host weld + ASCII PLY (path may be NULL: no file) */
+int mrh_extract_mesh(mrh_map* m, const char* path_or_null);
+/* GeoWrapper::getVertices / getFaces / getColors (geowrapper.h:91-93); pointers stay valid until the next extract */
+int mrh_get_mesh(mrh_map* m, const double** vertices, const int32_t** faces, const double** colors, size_t* n_vertices, size_t* n_faces);
+/* raw triangle soup of the last extract (72-byte Triangle records, voxel_hash_utils.cuh:46-64) */
+int mrh_get_triangles(mrh_map* m, const float** triangles, size_t* n_triangles);
+/* GeoWrapper::serializeData (geowrapper.cpp:563-565) */
+int mrh_serialize_data(mrh_map* m, const char* hash_path, const char* voxel_path);
+/* GeoWrapper::clearBuffers (geowrapper.cpp:552-557) */
+int mrh_clear_buffers(mrh_map* m);
+
+/* getters / setters of the sizing fields (geowrapper.h:79-109); names as in pygeowrapper.cpp:31-61 without get/set */
+int mrh_get_field(mrh_map* m, const char* name, double* out);
+int mrh_set_field(mrh_map* m, const char* name, double value);
+
+int mrh_get_stats(mrh_map* m, mrh_stats* out);
+int mrh_reset_stats(mrh_map* m);
+/* device time of the last compute() in ms (CUDAProfiler::CUDAEvent window, voxel_data_structures.cpp:94-109); synchronises */
+int mrh_last_compute_ms(mrh_map* m, float* ms);
+/* the CUDA stream compute() runs on (cudaStream_t), for event timing by the caller */
+int mrh_get_stream(mrh_map* m, void** stream);
+/* number of kernel launches issued by this handle so far */
+int mrh_get_launch_count(mrh_map* m, uint64_t* n);
+
+/* Parity dump: live block records sorted by (x, y, z) and their voxels as 12-byte reference Voxel
+ * structs {f32 sdf, f32 sum_squared, u8 r, g, b, weight} (512 per record; resolution-1 records use
+ * the first 64). Returns the number of live blocks in *n_out; fills at most max_entries. */
+int mrh_dump_state(mrh_map* m, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

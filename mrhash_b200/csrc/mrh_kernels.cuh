@@ -1,0 +1,707 @@
+// mrh_kernels.cuh — sm_100a kernels of the per-frame TSDF hot path (RGB-D).
+//
+// Replaces, for GeoWrapper::compute() (reference files under /root/reference/mrhash/src/sdf):
+//   k_alloc_rgbd      <- calculateCloudKernel (camera.cu:5-19) + allocBlocksKernel x(>=2) +
+//                        resetHashBucketMutexKernel + the host retry loop (voxel_data_structures.cu:758-922)
+//   k_visible         <- resetCompactHashTableKernel + flatAndReduceHashTableKernel(camera) (:9-14, :406-449)
+//   k_integrate       <- integrateDepthMapKernel (:1095-1181) + garbageCollectIdentifyKernel (:1674-1724)
+//                        [+ garbageCollectFreeKernel (:1827-1854) when FUSE_GC]
+//   k_starve          <- starveVoxelsKernel x2 (:1597-1671)
+//   k_identify        <- garbageCollectIdentifyKernel on starve / variance frames
+//   k_gc_free         <- garbageCollectFreeKernel + deleteHashEntryElement (:1727-1854)
+//
+// Data layout in HBM:
+//   keys[capacity] u64   packed block position (21 bits/axis, biased), EMPTY / TOMB sentinels;
+//                        bucket = 16 consecutive keys = one 128-byte line, bucket index =
+//                        calculateHash(pos) of the reference (voxel_data_structures.cu:151-160)
+//   vals[capacity] u32   pool block index (bit 31 = resolution 1, then index is a 64-voxel sub-slot)
+//   pool[num_blocks]     6144 B per block as three 2 KB planes: f32 sdf[512] | f32 sum_sq[512] |
+//                        u32 rgbw[512] (r | g<<8 | b<<16 | weight<<24) -> 128-bit coalesced access
+//   stats[num_blocks]    per pool block {min |sdf| over weight>0, max weight}: the GC predicate of
+//                        untouched blocks is answered without re-reading their payload
+//   heap[num_blocks]     free stack of pool indices (heap[i] = N-1-i initially, voxel_data_structures.cpp:58-69)
+//   live[2][num_blocks]  dense list of occupied table slots (double buffered, compacted per frame)
+//   vis[num_blocks]      per-frame list of in-frustum blocks (the reference's compact hash table)
+#pragma once
+#include "mrh_math.cuh"
+
+namespace mrh {
+
+constexpr unsigned long long kEmpty   = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long kTomb    = 0xFFFFFFFFFFFFFFFEull;
+constexpr unsigned long long kNoKey   = 0xFFFFFFFFFFFFFFFDull;
+constexpr uint32_t kInvalid           = 0xFFFFFFFFu;
+constexpr int kBucketSlots            = 16;
+constexpr int kMaxWindows             = 64; // 2 buckets per window
+constexpr uint32_t kBlockBytes        = 6144;
+constexpr uint32_t kPlaneBytes        = 2048;
+constexpr int kCoordBias              = 1 << 20;
+
+struct Counters {
+  int heap_counter;      // index of the stack top; free = heap_counter + 1 (voxel_data_structures.cpp:148-153)
+  int heap_low_counter;
+  uint32_t live_count[2];
+  uint32_t vis_count;
+  uint32_t n_realloc;
+  uint32_t n_reintegrate;
+  uint32_t pad0;
+  // per-run totals (read back on demand)
+  unsigned long long rays_valid;
+  unsigned long long blocks_new;
+  unsigned long long blocks_visible;
+  unsigned long long voxels_updated;
+  unsigned long long blocks_freed;
+  unsigned long long blocks_realloc;
+  unsigned long long dropped_heap;   // allocBlock "mem size exceed" events
+  unsigned long long dropped_table;  // probe sequence exhausted / coordinate out of key range
+};
+
+struct BlockStats {
+  float min_abs_sdf; // FLT_MAX when no voxel has weight > 0
+  uint32_t max_weight;
+};
+
+struct __align__(16) VisEntry {
+  int x, y, z;
+  uint32_t val;
+  uint32_t slot;
+  uint32_t live_idx;
+  uint32_t pad0, pad1;
+};
+
+struct FrameDev {
+  float R[9];
+  float t[3];
+  uint32_t frame_index;
+  uint32_t live_cur; // which live list is the input of this frame
+  uint32_t pad[2];
+};
+
+struct MapDev {
+  float voxel_size, trunc, trunc_scale, max_integration_distance;
+  float ext[3];
+  float gc_threshold; // host: trunc + scale * camera.maxDepth() (voxel_data_structures.cu:1720)
+  float var_threshold;
+  int weight_sample;
+  int min_weight_threshold;
+  int projective;
+  uint32_t num_buckets, capacity, num_blocks;
+  uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
+  unsigned long long* keys;
+  uint32_t* vals;
+  uint32_t* heap;
+  uint8_t* pool;
+  BlockStats* stats;
+  uint32_t* live[2];
+  VisEntry* vis;
+  unsigned long long* zbuf;
+  Counters* ctr;
+};
+
+__device__ __forceinline__ bool key_in_range(i3 b) {
+  return (unsigned) (b.x + kCoordBias) < (2u * kCoordBias) && (unsigned) (b.y + kCoordBias) < (2u * kCoordBias) &&
+         (unsigned) (b.z + kCoordBias) < (2u * kCoordBias);
+}
+__device__ __forceinline__ unsigned long long pack_key(i3 b) {
+  return ((unsigned long long) (unsigned) (b.x + kCoordBias) << 42) | ((unsigned long long) (unsigned) (b.y + kCoordBias) << 21) |
+         (unsigned long long) (unsigned) (b.z + kCoordBias);
+}
+__device__ __forceinline__ i3 unpack_key(unsigned long long k) {
+  return {(int) ((k >> 42) & 0x1FFFFF) - kCoordBias, (int) ((k >> 21) & 0x1FFFFF) - kCoordBias, (int) (k & 0x1FFFFF) - kCoordBias};
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void load_pose(const FrameDev& f, PoseDev& pose) {
+  for (int i = 0; i < 9; ++i)
+    pose.R[i] = f.R[i];
+  for (int i = 0; i < 3; ++i)
+    pose.t[i] = f.t[i];
+  pose_finish(pose);
+}
+
+// Single-thread lookup. Probe order: windows of two buckets starting at the home bucket; a window
+// that holds an EMPTY slot terminates the chain (inserts always take the first free slot in this
+// order and slots never return to EMPTY, so a present key sits before the first EMPTY).
+__device__ __forceinline__ int table_find(const MapDev& m, i3 b) {
+  if (!key_in_range(b))
+    return -1;
+  const unsigned long long key = pack_key(b);
+  const uint32_t h             = block_hash(b, m.num_buckets);
+#pragma unroll 1
+  for (int w = 0; w < kMaxWindows; ++w) {
+    bool has_empty = false;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t bkt       = (h + 2u * w + half) % m.num_buckets;
+      const ulonglong2* row    = reinterpret_cast<const ulonglong2*>(m.keys + (size_t) bkt * kBucketSlots);
+#pragma unroll
+      for (int i = 0; i < kBucketSlots / 2; ++i) {
+        const ulonglong2 k2 = row[i];
+        if (k2.x == key)
+          return (int) (bkt * kBucketSlots + 2 * i);
+        if (k2.y == key)
+          return (int) (bkt * kBucketSlots + 2 * i + 1);
+        has_empty |= (k2.x == kEmpty) | (k2.y == kEmpty);
+      }
+    }
+    if (has_empty)
+      return -1;
+  }
+  return -1;
+}
+
+// Warp-cooperative "insert if absent and in the enlarged frustum" of one block key.
+// All 32 lanes call this with the same b. Lane l inspects slot l of the current 32-slot window
+// (one 256-byte coalesced read), the match is resolved with ballots, the frustum test of a new
+// block is spread over lanes 0..7 (one corner each) and lane 0 claims the slot with one 64-bit CAS
+// on the key word: claim and key publication are a single atomic, so two warps racing on the same
+// key can never both insert it and no bucket mutex / host retry loop is needed.
+template <bool FRUSTUM_TEST>
+__device__ __forceinline__ void warp_insert(const MapDev& m, const CameraDev& cam, const PoseDev& pose, uint32_t live_cur, i3 b, int lane) {
+  const unsigned full = 0xFFFFFFFFu;
+  if (!key_in_range(b)) {
+    if (lane == 0)
+      atomicAdd(&m.ctr->dropped_table, 1ull);
+    return;
+  }
+  const uint32_t h = block_hash(b, m.num_buckets);
+  if (h < m.shard_lo || h >= m.shard_hi)
+    return; // another GPU owns this bucket range
+  const unsigned long long key = pack_key(b);
+  bool frustum_ok              = !FRUSTUM_TEST;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 1024; ++attempt) {
+    int free_slot                   = -1;
+    unsigned long long free_expected = kEmpty;
+    bool found = false, end = false;
+#pragma unroll 1
+    for (int w = 0; w < kMaxWindows && !end; ++w) {
+      const uint32_t bkt  = (h + 2u * w + (lane >> 4)) % m.num_buckets;
+      const uint32_t slot = bkt * kBucketSlots + (lane & 15);
+      const unsigned long long k = attempt == 0 ? m.keys[slot] : ld_cg_u64(m.keys + slot);
+      if (__ballot_sync(full, k == key)) {
+        found = true;
+        break;
+      }
+      const unsigned fr = __ballot_sync(full, k == kEmpty || k == kTomb);
+      const unsigned em = __ballot_sync(full, k == kEmpty);
+      if (free_slot < 0 && fr) {
+        const int src  = __ffs(fr) - 1;
+        free_slot      = (int) __shfl_sync(full, slot, src);
+        free_expected  = __shfl_sync(full, k, src);
+      }
+      end = em != 0;
+    }
+    if (found)
+      return;
+    if (free_slot < 0) {
+      if (lane == 0)
+        atomicAdd(&m.ctr->dropped_table, 1ull);
+      return;
+    }
+    if (!frustum_ok) {
+      const bool in = lane < 8 && block_corner_in_frustum(cam, pose, b, lane, m.voxel_size);
+      if (!__ballot_sync(full, in))
+        return;
+      frustum_ok = true;
+    }
+    unsigned long long prev = 0;
+    if (lane == 0)
+      prev = atomicCAS(m.keys + free_slot, free_expected, key);
+    prev = __shfl_sync(full, prev, 0);
+    if (prev == free_expected) {
+      if (lane == 0) {
+        const int addr = atomicSub(&m.ctr->heap_counter, 1); // consumeHeapHigh (:33-40)
+        if (addr < 0) {
+          atomicAdd(&m.ctr->heap_counter, 1);
+          atomicExch(m.keys + free_slot, kTomb);
+          atomicAdd(&m.ctr->dropped_heap, 1ull);
+        } else {
+          const uint32_t ptr = m.heap[addr];
+          m.vals[free_slot]  = ptr;
+          m.stats[ptr]       = {3.40282346638528859812e+38f, 0u};
+          const uint32_t cur = live_cur;
+          const uint32_t li  = atomicAdd(&m.ctr->live_count[cur], 1u);
+          m.live[cur][li]    = (uint32_t) free_slot;
+          atomicAdd(&m.ctr->blocks_new, 1ull);
+        }
+      }
+      return;
+    }
+    if (prev == key)
+      return; // another warp inserted the same key into the same slot first
+    // slot taken by a different key: rescan (reads now bypass L1)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_alloc_rgbd: one thread per pixel, one warp per 32-pixel row segment.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_alloc_rgbd(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth) {
+  __shared__ PoseDev pose;
+  if (threadIdx.x == 0) {
+    load_pose(f, pose);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      // lists consumed by later kernels of this frame start empty
+      m.ctr->live_count[f.live_cur ^ 1u] = 0;
+      m.ctr->vis_count                         = 0;
+    }
+  }
+  __syncthreads();
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane      = threadIdx.x & 31;
+  const int warp      = threadIdx.x >> 5;
+  const uint32_t col  = blockIdx.x * 32 + lane;
+  const uint32_t row  = blockIdx.y * 8 + warp;
+  bool active         = false;
+  DDA dda;
+  if (row < cam.rows && col < cam.cols) {
+    const float raw = __ldg(depth + (size_t) row * cam.cols + col);
+    const float d   = cloud_depth(cam, row, col, raw);
+    if (d != 0.f) {
+      const float t    = truncation(m.trunc, m.trunc_scale, d);
+      const float dmin = fminf(m.max_integration_distance, fsub(d, t));
+      const float dmax = fminf(m.max_integration_distance, fadd(d, t));
+      if (!(dmin >= dmax)) {
+        const f3 p0 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmin));
+        const f3 p1 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmax));
+        dda.init(p0, p1, m.voxel_size, m.ext, true);
+        active = true;
+      }
+    }
+  }
+  const unsigned n_rays = __popc(__ballot_sync(full, active));
+  if (lane == 0 && n_rays)
+    atomicAdd(&m.ctr->rays_valid, (unsigned long long) n_rays);
+  int iter = 0;
+  // Keys this warp has already resolved (present, inserted or rejected by the frustum test): the
+  // outcome cannot change within the frame, and neighbouring rays revisit the same few blocks.
+  unsigned long long recent[4] = {kNoKey, kNoKey, kNoKey, kNoKey};
+  int recent_pos               = 0;
+  while (__any_sync(full, active)) {
+    unsigned long long key = kNoKey;
+    bool want              = false;
+    if (active) {
+      if (key_in_range(dda.cur)) {
+        key  = pack_key(dda.cur);
+        want = key != recent[0] && key != recent[1] && key != recent[2] && key != recent[3];
+      } else {
+        atomicAdd(&m.ctr->dropped_table, 1ull);
+      }
+    }
+    // one leader per distinct unresolved key in the warp
+    const unsigned peers = __match_any_sync(full, want ? key : kNoKey);
+    const bool leader    = want && (lane == __ffs(peers) - 1);
+    unsigned todo        = __ballot_sync(full, leader);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const i3 b = {__shfl_sync(full, dda.cur.x, src), __shfl_sync(full, dda.cur.y, src), __shfl_sync(full, dda.cur.z, src)};
+      warp_insert<true>(m, cam, pose, f.live_cur, b, lane);
+      recent[recent_pos] = pack_key(b);
+      recent_pos         = (recent_pos + 1) & 3;
+    }
+    if (active) {
+      active = dda.advance();
+      if (++iter >= kMaxDDA)
+        active = false;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_visible: O(live) frustum pass over the dense live list (no full-table scan).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_visible(MapDev m, FrameDev f, CameraDev cam, int use_frustum) {
+  __shared__ PoseDev pose;
+  if (threadIdx.x == 0)
+    load_pose(f, pose);
+  __syncthreads();
+  const unsigned full  = 0xFFFFFFFFu;
+  const int lane       = threadIdx.x & 31;
+  const uint32_t cur   = f.live_cur;
+  const uint32_t n     = m.ctr->live_count[cur];
+  const uint32_t* in   = m.live[cur];
+  uint32_t* out        = m.live[cur ^ 1u];
+  const uint32_t n_pad = (n + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    uint32_t slot            = i < n ? in[i] : kInvalid;
+    unsigned long long key   = kEmpty;
+    if (slot != kInvalid)
+      key = m.keys[slot];
+    const bool alive = slot != kInvalid && key < kNoKey;
+    i3 b             = {0, 0, 0};
+    bool vis         = false;
+    if (alive) {
+      b   = unpack_key(key);
+      vis = use_frustum ? block_in_frustum(cam, pose, b, m.voxel_size) : true;
+    }
+    const unsigned am = __ballot_sync(full, alive);
+    const unsigned vm = __ballot_sync(full, vis);
+    uint32_t abase = 0, vbase = 0;
+    if (lane == 0) {
+      if (am)
+        abase = atomicAdd(&m.ctr->live_count[cur ^ 1u], (uint32_t) __popc(am));
+      if (vm)
+        vbase = atomicAdd(&m.ctr->vis_count, (uint32_t) __popc(vm));
+    }
+    abase                = __shfl_sync(full, abase, 0);
+    vbase                = __shfl_sync(full, vbase, 0);
+    const unsigned lt    = (1u << lane) - 1u;
+    const uint32_t my_li = abase + __popc(am & lt);
+    if (alive)
+      out[my_li] = slot;
+    if (vis) {
+      VisEntry e;
+      e.x = b.x, e.y = b.y, e.z = b.z;
+      e.val      = m.vals[slot];
+      e.slot     = slot;
+      e.live_idx = my_li;
+      e.pad0 = e.pad1 = 0;
+      m.vis[vbase + __popc(vm & lt)] = e;
+    }
+  }
+}
+
+// Remove a block from the map: tombstone its key, return its pool block to the free stack
+// (appendHeapHigh :52-56), drop it from the live list. Called by one thread.
+__device__ __forceinline__ void free_block(const MapDev& m, uint32_t live_cur, const VisEntry& e) {
+  atomicExch(m.keys + e.slot, kTomb);
+  const int addr   = atomicAdd(&m.ctr->heap_counter, 1);
+  m.heap[addr + 1] = e.val & 0x7FFFFFFFu;
+  m.live[live_cur ^ 1u][e.live_idx] = kInvalid;
+}
+
+__device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uint32_t max_w) {
+  return min_abs >= m.gc_threshold || max_w == 0u; // voxel_data_structures.cu:1711
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_integrate: one CTA (128 threads x 4 consecutive-x voxels) per visible block, persistent.
+// ---------------------------------------------------------------------------------------------
+template <bool FUSE_GC>
+__global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb) {
+  __shared__ PoseDev pose;
+  __shared__ float s_min[4];
+  __shared__ uint32_t s_max[4];
+  __shared__ uint32_t s_upd[4];
+  __shared__ int s_delete;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0)
+    load_pose(f, pose);
+  __syncthreads();
+  const uint32_t n_vis = m.ctr->vis_count;
+  const int lx0 = (tid & 1) * 4, ly = (tid >> 1) & 7, lz = tid >> 4;
+  const float half_size = fmul(m.voxel_size, 0.5f);
+  unsigned long long cta_updated = 0;
+  for (uint32_t bi = blockIdx.x; bi < n_vis; bi += gridDim.x) {
+    const VisEntry e = m.vis[bi];
+    if (e.val & 0x80000000u)
+      continue; // resolution-1 blocks are fused by k_integrate_lowres
+    // ---- pass 1: projection + depth test, registers only ----
+    float sdf_new[4];
+    uint32_t pix[4];
+    unsigned ok = 0;
+    const f3 pf_yz = {0.f, fmul(i2f(e.y * kBlockSide + ly), m.voxel_size), fmul(i2f(e.z * kBlockSide + lz), m.voxel_size)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f3 pf = {fmul(i2f(e.x * kBlockSide + lx0 + j), m.voxel_size), pf_yz.y, pf_yz.z};
+      const f3 pc = se3_mul(pose.Ri, pose.ti, pf);
+      int row, col;
+      sdf_new[j] = 0.f, pix[j] = 0;
+      if (project_point(cam, pc, row, col)) {
+        const uint32_t p = (uint32_t) row * cam.cols + (uint32_t) col;
+        const float d    = cloud_depth(cam, (uint32_t) row, (uint32_t) col, __ldg(depth + p));
+        if (d != 0.f && !(d > m.max_integration_distance)) {
+          float sdf     = fsub(d, get_depth(cam, pc));
+          const float t = truncation(m.trunc, m.trunc_scale, d);
+          if (!(sdf <= -t)) {
+            sdf        = (sdf >= 0.f) ? fminf(t, sdf) : fmaxf(-t, sdf);
+            sdf_new[j] = sdf;
+            pix[j]     = p;
+            ok |= 1u << j;
+          }
+        }
+      }
+    }
+    const int any = __syncthreads_or((int) ok);
+    float min_abs  = 3.40282346638528859812e+38f;
+    uint32_t max_w = 0, n_upd = 0;
+    uint8_t* base  = m.pool + (size_t) e.val * kBlockBytes;
+    float4 sdf4, ss4;
+    uint4 cw4;
+    if (any) {
+      // ---- pass 2: 128-bit loads of this thread's 4 voxels from the three planes ----
+      sdf4 = reinterpret_cast<const float4*>(base)[tid];
+      ss4  = reinterpret_cast<const float4*>(base + kPlaneBytes)[tid];
+      cw4  = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
+      float* sdfv    = reinterpret_cast<float*>(&sdf4);
+      float* ssv     = reinterpret_cast<float*>(&ss4);
+      uint32_t* cwv  = reinterpret_cast<uint32_t*>(&cw4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ok & (1u << j)) {
+          // integrateDepthMapKernel :1155-1180 + combineVoxel (voxel_hash_utils.cuh:169-181)
+          const uint32_t cw = cwv[j];
+          const uint32_t w0 = cw >> 24;
+          const uint8_t* px = rgb + (size_t) pix[j] * 3;
+          const uint32_t r1 = px[0], g1 = px[1], b1 = px[2];
+          uint32_t r0 = cw & 0xFF, g0 = (cw >> 8) & 0xFF, b0 = (cw >> 16) & 0xFF;
+          if (w0 == 0)
+            r0 = r1, g0 = g1, b0 = b1;
+          const float sdf       = sdf_new[j];
+          const float curr_mean = w0 > 0 ? sdfv[j] : sdf;
+          const float delta     = fdiv(fsub(sdf, curr_mean), half_size);
+          const uint32_t wsum   = w0 + (uint32_t) m.weight_sample;
+          const float merged    = fdiv(ffma(sdf, __uint2float_rn((uint32_t) m.weight_sample), fmul(sdfv[j], __uint2float_rn(w0))), __uint2float_rn(wsum));
+          const uint32_t rr     = (uint32_t) f2i(fadd(ffma(__uint2float_rn(r1), 0.5f, fmul(__uint2float_rn(r0), 0.5f)), 0.5f)) & 0xFF;
+          const uint32_t gg     = (uint32_t) f2i(fadd(ffma(__uint2float_rn(g1), 0.5f, fmul(__uint2float_rn(g0), 0.5f)), 0.5f)) & 0xFF;
+          const uint32_t bb     = (uint32_t) f2i(fadd(ffma(__uint2float_rn(b1), 0.5f, fmul(__uint2float_rn(b0), 0.5f)), 0.5f)) & 0xFF;
+          const uint32_t wn     = min(wsum, (uint32_t) kWeightMax);
+          const float delta2    = fdiv(fsub(sdf, merged), half_size);
+          float ss              = fmul(delta, delta2);
+          if (fabsf(ss) < 1.175494350822287508e-38f)
+            ss = 0.f; // ATOM.ADD.F32.FTZ of the reference flushes a denormal addend
+          sdfv[j] = merged;
+          ssv[j]  = fadd(0.f, ss); // Q1: merged_voxel starts from sum_squared = 0
+          cwv[j]  = rr | (gg << 8) | (bb << 16) | (wn << 24);
+          ++n_upd;
+        }
+        const uint32_t w = cwv[j] >> 24;
+        if (w != 0)
+          min_abs = fminf(min_abs, fabsf(sdfv[j]));
+        max_w = max(max_w, w);
+      }
+      // block-level reduction of the GC statistics
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        min_abs = fminf(min_abs, __shfl_xor_sync(0xFFFFFFFFu, min_abs, o));
+        max_w   = max(max_w, __shfl_xor_sync(0xFFFFFFFFu, max_w, o));
+        n_upd += __shfl_xor_sync(0xFFFFFFFFu, n_upd, o);
+      }
+      if (lane == 0)
+        s_min[warp] = min_abs, s_max[warp] = max_w, s_upd[warp] = n_upd;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      BlockStats st;
+      if (any) {
+        st.min_abs_sdf = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3]));
+        st.max_weight  = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+        cta_updated += s_upd[0] + s_upd[1] + s_upd[2] + s_upd[3];
+      } else {
+        st = m.stats[e.val];
+      }
+      int del = 0;
+      if (FUSE_GC) {
+        del = gc_predicate(m, st.min_abs_sdf, st.max_weight) ? 1 : 0;
+        if (del) {
+          free_block(m, f.live_cur, e);
+          atomicAdd(&m.ctr->blocks_freed, 1ull);
+          st.min_abs_sdf = 3.40282346638528859812e+38f;
+          st.max_weight  = 0;
+        }
+      }
+      if (any || del)
+        m.stats[e.val] = st;
+      s_delete = del;
+    }
+    __syncthreads();
+    const int del = FUSE_GC ? s_delete : 0;
+    if (del) {
+      // deleteVoxel over the whole block (:1838-1841): free pool blocks are always all-zero
+      const float4 z = {0.f, 0.f, 0.f, 0.f};
+      reinterpret_cast<float4*>(base)[tid]                   = z;
+      reinterpret_cast<float4*>(base + kPlaneBytes)[tid]     = z;
+      reinterpret_cast<float4*>(base + 2 * kPlaneBytes)[tid] = z;
+    } else if (ok) {
+      reinterpret_cast<float4*>(base)[tid]                  = sdf4;
+      reinterpret_cast<float4*>(base + kPlaneBytes)[tid]    = ss4;
+      reinterpret_cast<uint4*>(base + 2 * kPlaneBytes)[tid] = cw4;
+    }
+    __syncthreads(); // s_* reused by the next block of this CTA
+  }
+  if (tid == 0) {
+    if (cta_updated)
+      atomicAdd(&m.ctr->voxels_updated, cta_updated);
+    if (blockIdx.x == 0)
+      atomicAdd(&m.ctr->blocks_visible, (unsigned long long) n_vis);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// starve (every n-th frame): z-buffer pass then decrement pass
+// ---------------------------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(128) k_starve(MapDev m, FrameDev f, CameraDev cam) {
+  __shared__ PoseDev pose;
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    load_pose(f, pose);
+  __syncthreads();
+  const uint32_t n_vis = m.ctr->vis_count;
+  for (uint32_t bi = blockIdx.x; bi < n_vis; bi += gridDim.x) {
+    const VisEntry e = m.vis[bi];
+    if (e.val & 0x80000000u)
+      continue;
+    uint8_t* base = m.pool + (size_t) e.val * kBlockBytes;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int i  = tid * 4 + j;
+      const int lx = i & 7, ly = (i >> 3) & 7, lz = i >> 6;
+      const f3 pf  = {fmul(i2f(e.x * kBlockSide + lx), m.voxel_size), fmul(i2f(e.y * kBlockSide + ly), m.voxel_size),
+                      fmul(i2f(e.z * kBlockSide + lz), m.voxel_size)};
+      const f3 pc   = se3_mul(pose.Ri, pose.ti, pf);
+      const float d = get_depth(cam, pc);
+      if (d < cam.min_depth)
+        continue;
+      int row, col;
+      if (!project_point(cam, pc, row, col))
+        continue;
+      // pack(unique_tid, depth) (:1583-1585, :1629-1641)
+      const unsigned long long packed = ((unsigned long long) __float_as_uint(d) << 32) + (unsigned long long) (uint32_t) (kBlockVoxels * bi + i);
+      unsigned long long* cell = m.zbuf + (size_t) row * cam.cols + col;
+      if (PASS == 0) {
+        atomicMin(cell, packed);
+      } else if (*cell == packed) {
+        uint8_t* w = base + 2 * kPlaneBytes + 4 * i + 3;
+        *w         = (uint8_t) max(0, (int) *w - 1);
+      }
+    }
+  }
+}
+
+// recompute the GC statistics of every visible block from its payload (starve / variance frames)
+__global__ void __launch_bounds__(128) k_identify(MapDev m) {
+  __shared__ float s_min[4];
+  __shared__ uint32_t s_max[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_vis = m.ctr->vis_count;
+  for (uint32_t bi = blockIdx.x; bi < n_vis; bi += gridDim.x) {
+    const VisEntry e = m.vis[bi];
+    if (e.val & 0x80000000u)
+      continue;
+    const uint8_t* base = m.pool + (size_t) e.val * kBlockBytes;
+    const float4 sdf4   = reinterpret_cast<const float4*>(base)[tid];
+    const uint4 cw4     = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
+    const float sv[4]   = {sdf4.x, sdf4.y, sdf4.z, sdf4.w};
+    const uint32_t cv[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+    float min_abs  = 3.40282346638528859812e+38f;
+    uint32_t max_w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = cv[j] >> 24;
+      if (w)
+        min_abs = fminf(min_abs, fabsf(sv[j]));
+      max_w = max(max_w, w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      min_abs = fminf(min_abs, __shfl_xor_sync(0xFFFFFFFFu, min_abs, o));
+      max_w   = max(max_w, __shfl_xor_sync(0xFFFFFFFFu, max_w, o));
+    }
+    if (lane == 0)
+      s_min[warp] = min_abs, s_max[warp] = max_w;
+    __syncthreads();
+    if (tid == 0) {
+      BlockStats st;
+      st.min_abs_sdf = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3]));
+      st.max_weight  = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
+      m.stats[e.val] = st;
+    }
+    __syncthreads();
+  }
+}
+
+// apply the GC decision (stats must be current for every visible block)
+__global__ void __launch_bounds__(128) k_gc_free(MapDev m, FrameDev f) {
+  const int tid        = threadIdx.x;
+  const uint32_t n_vis = m.ctr->vis_count;
+  for (uint32_t bi = blockIdx.x; bi < n_vis; bi += gridDim.x) {
+    const VisEntry e = m.vis[bi];
+    if (e.val & 0x80000000u)
+      continue;
+    if (m.keys[e.slot] >= kNoKey)
+      continue; // already removed this frame (variance path)
+    const BlockStats st = m.stats[e.val];
+    if (!gc_predicate(m, st.min_abs_sdf, st.max_weight))
+      continue;
+    uint8_t* base  = m.pool + (size_t) e.val * kBlockBytes;
+    const float4 z = {0.f, 0.f, 0.f, 0.f};
+    reinterpret_cast<float4*>(base)[tid]                   = z;
+    reinterpret_cast<float4*>(base + kPlaneBytes)[tid]     = z;
+    reinterpret_cast<float4*>(base + 2 * kPlaneBytes)[tid] = z;
+    if (tid == 0) {
+      free_block(m, f.live_cur, e);
+      m.stats[e.val] = {3.40282346638528859812e+38f, 0u};
+      atomicAdd(&m.ctr->blocks_freed, 1ull);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gather_blocks: live list -> dense (record, AoS payload) buffers for streamAllOut /
+// serializeData / the parity dump (replaces the Streamer's integrateFromGlobalHashPass1/2,
+// streamer.cu:77-187: no per-thread serial prefix sums).
+// ---------------------------------------------------------------------------------------------
+struct GatherRecord {
+  int x, y, z, resolution, ptr;
+};
+
+__global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_cur, GatherRecord* records, uint32_t* voxels_aos, uint32_t* out_count, uint32_t max_out) {
+  __shared__ uint32_t s_out;
+  const int tid    = threadIdx.x;
+  const uint32_t n = m.ctr->live_count[live_cur];
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t slot = m.live[live_cur][i];
+    if (slot == kInvalid)
+      continue;
+    const unsigned long long key = m.keys[slot];
+    if (key >= kNoKey)
+      continue;
+    const uint32_t val = m.vals[slot];
+    if (tid == 0)
+      s_out = atomicAdd(out_count, 1u);
+    __syncthreads();
+    const uint32_t o = s_out;
+    __syncthreads();
+    if (o >= max_out)
+      continue;
+    const i3 b = unpack_key(key);
+    if (tid == 0)
+      records[o] = {b.x, b.y, b.z, (int) (val >> 31), (int) ((val & 0x7FFFFFFFu) * ((val >> 31) ? 64u : 512u))};
+    uint32_t* dst = voxels_aos + (size_t) o * kBlockVoxels * 3;
+    if (!(val >> 31)) {
+      const uint8_t* base = m.pool + (size_t) val * kBlockBytes;
+      const float4 sdf4   = reinterpret_cast<const float4*>(base)[tid];
+      const float4 ss4    = reinterpret_cast<const float4*>(base + kPlaneBytes)[tid];
+      const uint4 cw4     = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
+      const float sv[4] = {sdf4.x, sdf4.y, sdf4.z, sdf4.w}, qv[4] = {ss4.x, ss4.y, ss4.z, ss4.w};
+      const uint32_t cv[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dst[(tid * 4 + j) * 3 + 0] = __float_as_uint(sv[j]);
+        dst[(tid * 4 + j) * 3 + 1] = __float_as_uint(qv[j]);
+        dst[(tid * 4 + j) * 3 + 2] = cv[j];
+      }
+    } else {
+      // resolution 1: 64 voxels in a 768-byte sub-slot laid out as sdf[64] | sum_sq[64] | rgbw[64]
+      const uint8_t* base = m.pool + (size_t) (val & 0x7FFFFFFFu) * 768u;
+      for (int v = tid; v < kBlockVoxels; v += 128) {
+        uint32_t a = 0, b2 = 0, c = 0;
+        if (v < 64) {
+          a  = reinterpret_cast<const uint32_t*>(base)[v];
+          b2 = reinterpret_cast<const uint32_t*>(base + 256)[v];
+          c  = reinterpret_cast<const uint32_t*>(base + 512)[v];
+        }
+        dst[v * 3 + 0] = a, dst[v * 3 + 1] = b2, dst[v * 3 + 2] = c;
+      }
+    }
+  }
+}
+
+} // namespace mrh
