@@ -114,6 +114,8 @@ int mrh_synchronize(mrh_map* m);
 
 /* GeoWrapper::streamAllOut (geowrapper.cpp:559-561) */
 int mrh_stream_all_out(mrh_map* m);
+/* number of blocks currently held by the host store (the reference's Streamer::grid_) */
+int mrh_store_size(mrh_map* m, size_t* n_blocks);
 /* GeoWrapper::extractMesh (geowrapper.cpp:150-230): marching cubes + host weld + ASCII PLY (path may be NULL: no file) */
 int mrh_extract_mesh(mrh_map* m, const char* path_or_null);
 /* GeoWrapper::getVertices / getFaces / getColors (geowrapper.h:91-93); pointers stay valid until the next extract */

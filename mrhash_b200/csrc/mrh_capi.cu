@@ -1,0 +1,554 @@
+// mrh_capi.cu — host orchestration behind the C ABI of include/mrhash_b200.h.
+//
+// Replaces the host side of GeoWrapper::compute() (geowrapper.cpp:118-148) and
+// VoxelContainer::integrate() (voxel_data_structures.cpp:90-134): one stream, no host
+// synchronisation inside a frame, no per-frame allocation, pinned double-buffered ingest.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/mrhash_b200.h"
+#include "mrh_host.h"
+
+using namespace mrh;
+
+namespace mrh {
+  thread_local std::string g_last_error;
+
+  int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+  }
+} // namespace mrh
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));            \
+  } while (0)
+
+#define GUARD(m)                                                                                   \
+  if (!(m))                                                                                        \
+    return fail("null handle");                                                                    \
+  CK(cudaSetDevice((m)->device))
+
+// ---------------------------------------------------------------------------------------------
+// initialisation kernels (resetBuffers, voxel_data_structures.cpp:58-87, done on the device)
+// ---------------------------------------------------------------------------------------------
+namespace {
+  __global__ void k_init_heap(uint32_t* heap, BlockStats* stats, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      heap[i]  = n - 1u - i;
+      stats[i] = {FLT_MAX, 0u};
+    }
+  }
+  __global__ void k_init_counters(Counters* c, uint32_t n) {
+    Counters z;
+    memset(&z, 0, sizeof(z));
+    z.heap_counter     = (int) n - 1;
+    z.heap_low_counter = -1;
+    *c                 = z;
+  }
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+static int alloc_map(mrh_map* m) {
+  MapDev& d        = m->dev;
+  const uint64_t N = m->num_sdf_blocks, NB = m->hash_num_buckets;
+  if (N == 0 || NB == 0)
+    return fail("num_sdf_blocks / hash_num_buckets must be > 0");
+  if (N >= (1ull << 31) || NB * kBucketSlots >= (1ull << 32))
+    return fail("sizing exceeds 32-bit slot / pool indices (num_sdf_blocks=%llu, hash_num_buckets=%llu)", (unsigned long long) N, (unsigned long long) NB);
+  d.num_blocks  = (uint32_t) N;
+  d.num_buckets = (uint32_t) NB;
+  d.capacity    = (uint32_t) (NB * kBucketSlots);
+  CK(cudaMalloc(&d.keys, sizeof(unsigned long long) * d.capacity));
+  CK(cudaMalloc(&d.vals, sizeof(uint32_t) * d.capacity));
+  CK(cudaMalloc(&d.heap, sizeof(uint32_t) * N));
+  CK(cudaMalloc(&d.heap_low, sizeof(uint32_t) * N * 8));
+  CK(cudaMalloc(&d.pool, (size_t) kBlockBytes * N));
+  CK(cudaMalloc(&d.stats, sizeof(BlockStats) * N));
+  CK(cudaMalloc(&d.live[0], sizeof(uint32_t) * N * 2));
+  CK(cudaMalloc(&d.live[1], sizeof(uint32_t) * N * 2));
+  CK(cudaMalloc(&d.vis, sizeof(VisEntry) * N * 2));
+  CK(cudaMalloc(&d.realloc_list, sizeof(VisEntry) * N));
+  CK(cudaMalloc(&d.ctr, sizeof(Counters)));
+  return 0;
+}
+
+int mrh::reset_map(mrh_map* m) {
+  MapDev& d = m->dev;
+  CK(cudaMemsetAsync(d.keys, 0xFF, sizeof(unsigned long long) * d.capacity, m->stream));
+  CK(cudaMemsetAsync(d.vals, 0xFF, sizeof(uint32_t) * d.capacity, m->stream));
+  CK(cudaMemsetAsync(d.pool, 0, (size_t) kBlockBytes * d.num_blocks, m->stream));
+  k_init_heap<<<592, 256, 0, m->stream>>>(d.heap, d.stats, d.num_blocks);
+  k_init_counters<<<1, 1, 0, m->stream>>>(d.ctr, d.num_blocks);
+  m->launches += 2;
+  m->live_cur = 0;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static void free_map(mrh_map* m) {
+  MapDev& d = m->dev;
+  cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.stats);
+  cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.ctr), cudaFree(d.zbuf);
+  cudaFree(m->d_depth), cudaFree(m->d_rgb), cudaFree(m->d_points);
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(m->h_depth[i]), cudaFreeHost(m->h_rgb[i]), cudaFreeHost(m->h_points[i]);
+    if (m->ev_depth[i])
+      cudaEventDestroy(m->ev_depth[i]);
+    if (m->ev_rgb[i])
+      cudaEventDestroy(m->ev_rgb[i]);
+    if (m->ev_points[i])
+      cudaEventDestroy(m->ev_points[i]);
+  }
+  cudaFree(m->d_tri), cudaFree(m->d_tri_count);
+  cudaFreeHost(m->h_ctr);
+  if (m->ev0)
+    cudaEventDestroy(m->ev0);
+  if (m->ev1)
+    cudaEventDestroy(m->ev1);
+  if (m->stream)
+    cudaStreamDestroy(m->stream);
+}
+
+static void refresh_map_params(mrh_map* m) {
+  MapDev& d                  = m->dev;
+  const mrh_params& p        = m->p;
+  d.voxel_size               = p.virtual_voxel_size;
+  d.trunc                    = p.sdf_truncation;
+  d.trunc_scale              = p.sdf_truncation_scale;
+  d.max_integration_distance = m->max_integration_distance;
+  d.ext[0] = d.ext[1] = d.ext[2] = (float) p.voxel_extents_scale;
+  // host getTruncation(camera.maxDepth()) (voxel_data_structures.cu:1720): g++ host code, two roundings
+  volatile float prod = p.sdf_truncation_scale * m->cam.max_depth;
+  d.gc_threshold      = p.sdf_truncation + prod;
+  d.var_threshold     = p.sdf_var_threshold;
+  d.weight_sample     = p.integration_weight_sample;
+  d.min_weight_threshold = p.min_weight_threshold;
+  d.projective           = p.projective_sdf;
+  d.mc_threshold         = p.marching_cubes_threshold;
+  if (p.shard_world > 1) {
+    d.shard_lo = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) p.shard_rank / (uint64_t) p.shard_world);
+    d.shard_hi = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) (p.shard_rank + 1) / (uint64_t) p.shard_world);
+  } else {
+    d.shard_lo = 0, d.shard_hi = d.num_buckets;
+  }
+}
+
+// Ingest: copy into one of two pinned staging buffers and queue the H2D copy immediately, so the
+// transfer of frame k+1 overlaps the kernels of frame k (the reference does a blocking
+// DualMatrix::toDevice inside compute(), cuda_matrix.cuh:129).
+template <typename T, typename F>
+static int stage_upload(mrh_map* m, T** h_buf, size_t* h_cap, cudaEvent_t* ev, int* which, T** d_buf, size_t* d_cap, size_t n, F fill) {
+  if (n > *d_cap) {
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(*d_buf);
+    *d_buf = nullptr;
+    CK(cudaMalloc(d_buf, sizeof(T) * n));
+    *d_cap = n;
+  }
+  const int w = *which ^= 1;
+  if (n > h_cap[w]) {
+    CK(cudaEventSynchronize(ev[w]));
+    cudaFreeHost(h_buf[w]);
+    h_buf[w] = nullptr;
+    CK(cudaMallocHost(&h_buf[w], sizeof(T) * n));
+    h_cap[w] = n;
+  }
+  CK(cudaEventSynchronize(ev[w])); // the copy that last read this staging buffer has finished
+  fill(h_buf[w]);
+  CK(cudaMemcpyAsync(*d_buf, h_buf[w], sizeof(T) * n, cudaMemcpyHostToDevice, m->stream));
+  CK(cudaEventRecord(ev[w], m->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mrh_last_error(void) {
+  return g_last_error.c_str();
+}
+int mrh_abi_version(void) {
+  return MRH_ABI_VERSION;
+}
+
+int mrh_params_default(mrh_params* p) {
+  if (!p)
+    return fail("null params");
+  memset(p, 0, sizeof(*p));
+  // configurations/replica.cfg:1-18
+  p->sdf_truncation             = 0.07f;
+  p->sdf_truncation_scale       = 0.f;
+  p->integration_weight_sample  = 1;
+  p->virtual_voxel_size         = 0.01f;
+  p->n_frames_invalidate_voxels = 100;
+  p->voxel_extents_scale        = 1;
+  p->marching_cubes_threshold   = 1.5f;
+  p->min_weight_threshold       = 5;
+  p->min_depth                  = 0.01f;
+  p->max_depth                  = 30.f;
+  p->projective_sdf             = 1;
+  p->device                     = -1;
+  return 0;
+}
+
+int mrh_create(const mrh_params* p, mrh_map** out) {
+  if (!p || !out)
+    return fail("null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: libmrhash_b200 has no CPU path");
+  int dev = p->device;
+  if (dev < 0)
+    CK(cudaGetDevice(&dev));
+  CK(cudaSetDevice(dev));
+  mrh_map* m = new mrh_map();
+  m->p       = *p;
+  m->device  = dev;
+  CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&m->ev0));
+  CK(cudaEventCreate(&m->ev1));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&m->ev_depth[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_rgb[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&m->ev_points[i], cudaEventDisableTiming));
+  }
+  CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  m->num_sms = prop.multiProcessorCount;
+
+  // sizing: geowrapper.cpp:37-54 with params.h:33-37 ratios, in 64-bit arithmetic
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const double to_alloc = (double) free_b * 0.70;
+  uint64_t nblocks      = p->num_sdf_blocks ? p->num_sdf_blocks : (uint64_t) (to_alloc * 0.70 / (12.0 * 512.0));
+  if (!p->num_sdf_blocks)
+    nblocks = std::min<uint64_t>(nblocks, (1ull << 31) - 1);
+  uint64_t nbuckets = p->hash_num_buckets ? p->hash_num_buckets : nblocks;
+  nbuckets          = std::min<uint64_t>(nbuckets, ((1ull << 32) - 1) / kBucketSlots);
+  uint64_t ntri     = p->max_num_triangles ? p->max_num_triangles : (uint64_t) (to_alloc * 0.25 / 72.0);
+  m->num_sdf_blocks    = nblocks;
+  m->hash_num_buckets  = nbuckets;
+  m->max_num_triangles = ntri;
+  m->max_stream_blocks = (uint64_t) (to_alloc * 0.10 / (12.0 * 512.0));
+  if (alloc_map(m)) {
+    free_map(m);
+    delete m;
+    return 1;
+  }
+  // geowrapper.cpp:80: default 1x1 spherical camera
+  static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memcpy(m->pose, I, sizeof(I));
+  memcpy(m->cam_in_lidar, I, sizeof(I));
+  if (mrh_set_camera(m, 1.f, 1.f, 0.f, 0.f, 1, 1, p->min_depth, p->max_depth, 1) || reset_map(m)) {
+    free_map(m);
+    delete m;
+    return 1;
+  }
+  CK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return 0;
+}
+
+int mrh_destroy(mrh_map* m) {
+  if (!m)
+    return 0;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  free_map(m);
+  delete m;
+  return 0;
+}
+
+int mrh_set_camera(mrh_map* m, float fx, float fy, float cx, float cy, int rows, int cols, float min_depth, float max_depth, int camera_model) {
+  GUARD(m);
+  if (rows <= 0 || cols <= 0)
+    return fail("mrh_set_camera: rows/cols must be positive");
+  if (camera_model != 0 && camera_model != 1)
+    return fail("mrh_set_camera: camera_model must be 0 (pinhole) or 1 (spherical)");
+  CameraDev& c = m->cam;
+  // camera.cuh:13-39
+  c.fx = fx, c.fy = fy, c.ifx = 1.f / fx, c.ify = 1.f / fy, c.cx = cx, c.cy = cy;
+  c.rows = (uint32_t) rows, c.cols = (uint32_t) cols;
+  c.row_thr   = (int) ((float) rows * 0.5f);
+  c.col_thr   = (int) ((float) cols * 0.5f);
+  c.min_depth = min_depth, c.max_depth = max_depth, c.model = camera_model;
+  m->max_integration_distance = max_depth; // setIntegrationDistance (geowrapper.cpp:111)
+  const size_t npix           = (size_t) rows * cols;
+  if (npix > m->zbuf_cap) {
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(m->dev.zbuf);
+    CK(cudaMalloc(&m->dev.zbuf, sizeof(unsigned long long) * npix));
+    m->zbuf_cap = npix;
+  }
+  refresh_map_params(m);
+  return 0;
+}
+
+int mrh_set_pose_matrix(mrh_map* m, const float T[16]) {
+  if (!m || !T)
+    return fail("null argument");
+  memcpy(m->pose, T, sizeof(float) * 16);
+  return 0;
+}
+
+int mrh_set_pose(mrh_map* m, const float t[3], const float q[4]) {
+  if (!m || !t || !q)
+    return fail("null argument");
+  // Eigen::Quaternionf(w, x, y, z).toRotationMatrix() in float, no normalisation (geowrapper.cpp:86-92)
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  float* o = m->pose;
+  o[0] = 1.f - (tyy + tzz), o[1] = txy - twz, o[2] = txz + twy, o[3] = t[0];
+  o[4] = txy + twz, o[5] = 1.f - (txx + tzz), o[6] = tyz - twx, o[7] = t[1];
+  o[8] = txz - twy, o[9] = tyz + twx, o[10] = 1.f - (txx + tyy), o[11] = t[2];
+  o[12] = o[13] = o[14] = 0.f, o[15] = 1.f;
+  return 0;
+}
+
+int mrh_get_pose_matrix(mrh_map* m, float out[16]) {
+  if (!m || !out)
+    return fail("null argument");
+  memcpy(out, m->pose, sizeof(float) * 16);
+  return 0;
+}
+
+int mrh_set_camera_in_lidar(mrh_map* m, const float T[16]) {
+  if (!m || !T)
+    return fail("null argument");
+  memcpy(m->cam_in_lidar, T, sizeof(float) * 16);
+  return 0;
+}
+
+int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols) {
+  GUARD(m);
+  if (!depth || rows <= 0 || cols <= 0)
+    return fail("GeoWrapper::setDepthImage|input should be a 2D numpy array");
+  const size_t n = (size_t) rows * cols;
+  if (stage_upload(m, m->h_depth, m->h_depth_cap, m->ev_depth, &m->depth_which, &m->d_depth, &m->d_depth_cap, n, [&](float* dst) { memcpy(dst, depth, sizeof(float) * n); }))
+    return 1;
+  m->depth_ptr = m->d_depth, m->depth_rows = rows, m->depth_cols = cols;
+  m->h2d_bytes += sizeof(float) * n;
+  return 0;
+}
+
+int mrh_set_rgb(mrh_map* m, const uint8_t* rgb, int rows, int cols) {
+  GUARD(m);
+  if (!rgb || rows <= 0 || cols <= 0)
+    return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
+  const size_t n = (size_t) rows * cols * 3;
+  if (stage_upload(m, m->h_rgb, m->h_rgb_cap, m->ev_rgb, &m->rgb_which, &m->d_rgb, &m->d_rgb_cap, n, [&](uint8_t* dst) { memcpy(dst, rgb, n); }))
+    return 1;
+  m->rgb_ptr = m->d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
+  m->h2d_bytes += n;
+  return 0;
+}
+
+int mrh_set_rgb_f32(mrh_map* m, const float* rgb, int rows, int cols) {
+  GUARD(m);
+  if (!rgb || rows <= 0 || cols <= 0)
+    return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
+  const size_t n = (size_t) rows * cols * 3;
+  if (stage_upload(m, m->h_rgb, m->h_rgb_cap, m->ev_rgb, &m->rgb_which, &m->d_rgb, &m->d_rgb_cap, n, [&](uint8_t* dst) {
+        for (size_t i = 0; i < n; ++i)
+          dst[i] = (uint8_t) rgb[i];
+      }))
+    return 1;
+  m->rgb_ptr = m->d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
+  m->h2d_bytes += n;
+  return 0;
+}
+
+int mrh_set_depth_device(mrh_map* m, const float* d_depth, int rows, int cols) {
+  if (!m || !d_depth || rows <= 0 || cols <= 0)
+    return fail("mrh_set_depth_device: bad argument");
+  m->depth_ptr = d_depth, m->depth_rows = rows, m->depth_cols = cols;
+  return 0;
+}
+
+int mrh_set_rgb_device(mrh_map* m, const uint8_t* d_rgb, int rows, int cols) {
+  if (!m || !d_rgb || rows <= 0 || cols <= 0)
+    return fail("mrh_set_rgb_device: bad argument");
+  m->rgb_ptr = d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
+  return 0;
+}
+
+int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* normals) {
+  GUARD(m);
+  (void) normals; // projective sdf ignores normals (voxel_data_structures.cu:1317-1319)
+  if (!points && n)
+    return fail("GeoWrapper::setPointCloud|input should be a 2D numpy array");
+  if (n == 0) {
+    m->n_points = 0;
+    return 0;
+  }
+  if (!m->p.projective_sdf)
+    return fail("mrh_set_points: only projective_sdf=True is implemented (every shipped runner uses it)");
+  if (stage_upload(m, m->h_points, m->h_points_cap, m->ev_points, &m->points_which, &m->d_points, &m->d_points_cap, n * 3, [&](float* dst) { memcpy(dst, points, sizeof(float) * n * 3); }))
+    return 1;
+  m->n_points = n;
+  m->h_points_last = m->h_points[m->points_which];
+  m->h2d_bytes += sizeof(float) * 3 * n;
+  return 0;
+}
+
+int mrh_compute(mrh_map* m) {
+  GUARD(m);
+  const bool rgbd = m->depth_ptr && m->rgb_ptr;
+  if (rgbd) {
+    if (m->depth_rows != (int) m->cam.rows || m->depth_cols != (int) m->cam.cols || m->rgb_rows != m->depth_rows || m->rgb_cols != m->depth_cols)
+      return fail("mrh_compute: depth %dx%d / rgb %dx%d do not match the camera %ux%u", m->depth_rows, m->depth_cols, m->rgb_rows, m->rgb_cols, m->cam.rows, m->cam.cols);
+  }
+  refresh_map_params(m);
+  CK(cudaEventRecord(m->ev0, m->stream));
+  if (rgbd && integrate_rgbd(m))
+    return 1;
+  if (m->n_points && integrate_points(m))
+    return 1;
+  CK(cudaEventRecord(m->ev1, m->stream));
+  return 0;
+}
+
+int mrh_synchronize(mrh_map* m) {
+  GUARD(m);
+  CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int mrh_clear_buffers(mrh_map* m) {
+  GUARD(m);
+  if (mrh_stream_all_out(m))
+    return 1;
+  m->store.clear();
+  return 0;
+}
+
+int mrh_get_field(mrh_map* m, const char* name, double* out) {
+  if (!m || !name || !out)
+    return fail("null argument");
+  const std::string n(name);
+  const mrh_params& p = m->p;
+  // pygeowrapper.cpp:31-61
+  if (n == "SDFTruncation") *out = p.sdf_truncation;
+  else if (n == "SDFTruncationScale") *out = p.sdf_truncation_scale;
+  else if (n == "IntegrationWeightSample") *out = p.integration_weight_sample;
+  else if (n == "IntegrationWeightMax") *out = kWeightMax;
+  else if (n == "VirtualVoxelSize") *out = p.virtual_voxel_size;
+  else if (n == "NumSDFBlocks") *out = (double) m->num_sdf_blocks;
+  else if (n == "HashNumBuckets") *out = (double) m->hash_num_buckets;
+  else if (n == "HashBucketSize") *out = 10; // params.h:12 (the reference's logical bucket size)
+  else if (n == "LinkedListSize") *out = 7;  // params.h:13
+  else if (n == "NFramesInvalidateVoxels") *out = p.n_frames_invalidate_voxels;
+  else if (n == "VoxelExtentsScale") *out = p.voxel_extents_scale;
+  else if (n == "MaxNumSdfBlockIntegrateFromGlobalHash") *out = (double) m->max_stream_blocks;
+  else if (n == "MaxNumTrianglesMesh") *out = (double) m->max_num_triangles;
+  else if (n == "MinWeightThreshold") *out = p.min_weight_threshold;
+  else if (n == "SDFVarThreshold") *out = p.sdf_var_threshold;
+  else if (n == "VerticesMergingThreshold") *out = p.vertices_merging_threshold;
+  else if (n == "MarchingCubesThreshold") *out = p.marching_cubes_threshold;
+  else
+    return fail("mrh_get_field: unknown field '%s'", name);
+  return 0;
+}
+
+int mrh_set_field(mrh_map* m, const char* name, double v) {
+  if (!m || !name)
+    return fail("null argument");
+  const std::string n(name);
+  mrh_params& p = m->p;
+  // The reference's setters only change GeoWrapper's own fields after the container has been
+  // built (geowrapper.h:98-109), so the getters reflect them but the map does not; same here for
+  // the sizing fields. The fusion parameters are the exception we keep live (read every frame).
+  if (n == "SDFTruncation") p.sdf_truncation = (float) v;
+  else if (n == "SDFTruncationScale") p.sdf_truncation_scale = (float) v;
+  else if (n == "IntegrationWeightSample") p.integration_weight_sample = (int) v;
+  else if (n == "IntegrationWeightMax") return 0;
+  else if (n == "VirtualVoxelSize") return fail("mrh_set_field: VirtualVoxelSize cannot change after construction");
+  else if (n == "NumSDFBlocks" || n == "HashNumBuckets" || n == "HashBucketSize" || n == "LinkedListSize" || n == "MaxNumTrianglesMesh") return 0;
+  else if (n == "NFramesInvalidateVoxels") p.n_frames_invalidate_voxels = (int) v;
+  else if (n == "VoxelExtentsScale") return 0;
+  else if (n == "MinWeightThreshold") p.min_weight_threshold = (int) v;
+  else if (n == "SDFVarThreshold") p.sdf_var_threshold = (float) v;
+  else if (n == "VerticesMergingThreshold") p.vertices_merging_threshold = (float) v;
+  else if (n == "MarchingCubesThreshold") p.marching_cubes_threshold = (float) v;
+  else
+    return fail("mrh_set_field: unknown field '%s'", name);
+  refresh_map_params(m);
+  return 0;
+}
+
+int mrh_get_stats(mrh_map* m, mrh_stats* out) {
+  GUARD(m);
+  if (!out)
+    return fail("null argument");
+  CK(cudaMemcpyAsync(m->h_ctr, m->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  const Counters& c   = *m->h_ctr;
+  out->frames         = m->frames_total;
+  out->rays_valid     = c.rays_valid;
+  out->blocks_new     = c.blocks_new;
+  out->blocks_visible = c.blocks_visible;
+  out->voxels_updated = c.voxels_updated;
+  out->blocks_freed   = c.blocks_freed;
+  out->blocks_realloc = c.blocks_realloc;
+  out->dropped_heap   = c.dropped_heap;
+  out->dropped_table  = c.dropped_table;
+  out->live_blocks    = (uint64_t) ((int64_t) m->num_sdf_blocks - ((int64_t) c.heap_counter + 1)) - c.low_parents + c.low_live;
+  out->heap_free      = (int64_t) c.heap_counter + 1;
+  out->heap_low_free  = (int64_t) c.heap_low_counter + 1;
+  return 0;
+}
+
+int mrh_reset_stats(mrh_map* m) {
+  GUARD(m);
+  const size_t off = offsetof(Counters, rays_valid);
+  CK(cudaMemsetAsync((char*) m->dev.ctr + off, 0, offsetof(Counters, low_parents) - off, m->stream));
+  m->frames_total = 0;
+  m->h2d_bytes    = 0;
+  return 0;
+}
+
+int mrh_last_compute_ms(mrh_map* m, float* ms) {
+  GUARD(m);
+  if (!ms)
+    return fail("null argument");
+  CK(cudaEventSynchronize(m->ev1));
+  CK(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return 0;
+}
+
+int mrh_get_stream(mrh_map* m, void** stream) {
+  if (!m || !stream)
+    return fail("null argument");
+  *stream = (void*) m->stream;
+  return 0;
+}
+
+int mrh_get_launch_count(mrh_map* m, uint64_t* n) {
+  if (!m || !n)
+    return fail("null argument");
+  *n = m->launches;
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,103 @@
+// mrh_host.h — host-side state of one map handle (shared by the translation units of libmrhash_b200).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mrhash_b200.h"
+#include "mrh_types.cuh"
+
+namespace mrh {
+
+  // Host store of streamed-out blocks: the role of Streamer::grid_ (streamer.cuh:354, the
+  // unordered_map of 1 m chunks filled by integrateInChunkGrid, streamer.cpp:216-247). Records are
+  // kept dense; the chunk of a record is derived on demand (worldToChunks of the block origin).
+  struct HostStore {
+    std::vector<GatherRecord> recs;
+    std::vector<uint32_t> voxels; // 512 x {sdf bits, sum_squared bits, rgbw} per record (reference Voxel layout)
+    void clear() {
+      recs.clear();
+      voxels.clear();
+      recs.shrink_to_fit();
+      voxels.shrink_to_fit();
+    }
+    size_t size() const {
+      return recs.size();
+    }
+  };
+
+  struct HostMesh {
+    std::vector<float> triangles; // raw soup of the last extraction, 18 floats per triangle
+    std::vector<double> vertices; // V x 3
+    std::vector<int32_t> faces;   // F x 3
+    std::vector<double> colors;   // V x 3
+  };
+
+  int fail(const char* fmt, ...);
+
+} // namespace mrh
+
+struct mrh_map {
+  mrh_params p{};
+  int device  = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mrh::MapDev dev{};
+  mrh::CameraDev cam{};
+  float pose[16]{};
+  float cam_in_lidar[16]{};
+  float max_integration_distance = 0.f;
+  uint64_t num_sdf_blocks = 0, hash_num_buckets = 0, max_num_triangles = 0, max_stream_blocks = 0;
+  size_t zbuf_cap = 0;
+
+  // ingest (pinned, double buffered)
+  float* h_depth[2]{};
+  size_t h_depth_cap[2]{};
+  cudaEvent_t ev_depth[2]{};
+  int depth_which = 0;
+  uint8_t* h_rgb[2]{};
+  size_t h_rgb_cap[2]{};
+  cudaEvent_t ev_rgb[2]{};
+  int rgb_which = 0;
+  float* h_points[2]{};
+  size_t h_points_cap[2]{};
+  cudaEvent_t ev_points[2]{};
+  int points_which     = 0;
+  float* h_points_last = nullptr;
+  float* d_depth       = nullptr;
+  size_t d_depth_cap   = 0;
+  uint8_t* d_rgb       = nullptr;
+  size_t d_rgb_cap     = 0;
+  float* d_points      = nullptr;
+  size_t d_points_cap  = 0;
+  const float* depth_ptr = nullptr;
+  const uint8_t* rgb_ptr = nullptr;
+  int depth_rows = 0, depth_cols = 0, rgb_rows = 0, rgb_cols = 0;
+  size_t n_points = 0;
+
+  uint32_t frame_index = 0; // num_integrated_frames_ (voxel_data_structures.cpp:106)
+  uint32_t live_cur    = 0;
+  uint64_t frames_total = 0;
+  uint64_t launches     = 0;
+  uint64_t h2d_bytes    = 0;
+  mrh::Counters* h_ctr  = nullptr; // pinned read-back
+
+  // meshing
+  float* d_tri           = nullptr;
+  size_t d_tri_cap       = 0;
+  uint32_t* d_tri_count  = nullptr;
+  mrh::HostStore store;
+  mrh::HostMesh mesh;
+};
+
+namespace mrh {
+  int reset_map(mrh_map* m);
+  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels);
+  int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
+  int integrate_rgbd(mrh_map* m);
+  int integrate_points(mrh_map* m);
+  FrameDev make_frame(const mrh_map* m);
+} // namespace mrh

@@ -10,233 +10,10 @@
 //   k_identify        <- garbageCollectIdentifyKernel on starve / variance frames
 //   k_gc_free         <- garbageCollectFreeKernel + deleteHashEntryElement (:1727-1854)
 //
-// Data layout in HBM:
-//   keys[capacity] u64   packed block position (21 bits/axis, biased), EMPTY / TOMB sentinels;
-//                        bucket = 16 consecutive keys = one 128-byte line, bucket index =
-//                        calculateHash(pos) of the reference (voxel_data_structures.cu:151-160)
-//   vals[capacity] u32   pool block index (bit 31 = resolution 1, then index is a 64-voxel sub-slot)
-//   pool[num_blocks]     6144 B per block as three 2 KB planes: f32 sdf[512] | f32 sum_sq[512] |
-//                        u32 rgbw[512] (r | g<<8 | b<<16 | weight<<24) -> 128-bit coalesced access
-//   stats[num_blocks]    per pool block {min |sdf| over weight>0, max weight}: the GC predicate of
-//                        untouched blocks is answered without re-reading their payload
-//   heap[num_blocks]     free stack of pool indices (heap[i] = N-1-i initially, voxel_data_structures.cpp:58-69)
-//   live[2][num_blocks]  dense list of occupied table slots (double buffered, compacted per frame)
-//   vis[num_blocks]      per-frame list of in-frustum blocks (the reference's compact hash table)
 #pragma once
-#include "mrh_math.cuh"
+#include "mrh_table.cuh"
 
 namespace mrh {
-
-constexpr unsigned long long kEmpty   = 0xFFFFFFFFFFFFFFFFull;
-constexpr unsigned long long kTomb    = 0xFFFFFFFFFFFFFFFEull;
-constexpr unsigned long long kNoKey   = 0xFFFFFFFFFFFFFFFDull;
-constexpr uint32_t kInvalid           = 0xFFFFFFFFu;
-constexpr int kBucketSlots            = 16;
-constexpr int kMaxWindows             = 64; // 2 buckets per window
-constexpr uint32_t kBlockBytes        = 6144;
-constexpr uint32_t kPlaneBytes        = 2048;
-constexpr int kCoordBias              = 1 << 20;
-
-struct Counters {
-  int heap_counter;      // index of the stack top; free = heap_counter + 1 (voxel_data_structures.cpp:148-153)
-  int heap_low_counter;
-  uint32_t live_count[2];
-  uint32_t vis_count;
-  uint32_t n_realloc;
-  uint32_t n_reintegrate;
-  uint32_t pad0;
-  // per-run totals (read back on demand)
-  unsigned long long rays_valid;
-  unsigned long long blocks_new;
-  unsigned long long blocks_visible;
-  unsigned long long voxels_updated;
-  unsigned long long blocks_freed;
-  unsigned long long blocks_realloc;
-  unsigned long long dropped_heap;   // allocBlock "mem size exceed" events
-  unsigned long long dropped_table;  // probe sequence exhausted / coordinate out of key range
-};
-
-struct BlockStats {
-  float min_abs_sdf; // FLT_MAX when no voxel has weight > 0
-  uint32_t max_weight;
-};
-
-struct __align__(16) VisEntry {
-  int x, y, z;
-  uint32_t val;
-  uint32_t slot;
-  uint32_t live_idx;
-  uint32_t pad0, pad1;
-};
-
-struct FrameDev {
-  float R[9];
-  float t[3];
-  uint32_t frame_index;
-  uint32_t live_cur; // which live list is the input of this frame
-  uint32_t pad[2];
-};
-
-struct MapDev {
-  float voxel_size, trunc, trunc_scale, max_integration_distance;
-  float ext[3];
-  float gc_threshold; // host: trunc + scale * camera.maxDepth() (voxel_data_structures.cu:1720)
-  float var_threshold;
-  int weight_sample;
-  int min_weight_threshold;
-  int projective;
-  uint32_t num_buckets, capacity, num_blocks;
-  uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
-  unsigned long long* keys;
-  uint32_t* vals;
-  uint32_t* heap;
-  uint8_t* pool;
-  BlockStats* stats;
-  uint32_t* live[2];
-  VisEntry* vis;
-  unsigned long long* zbuf;
-  Counters* ctr;
-};
-
-__device__ __forceinline__ bool key_in_range(i3 b) {
-  return (unsigned) (b.x + kCoordBias) < (2u * kCoordBias) && (unsigned) (b.y + kCoordBias) < (2u * kCoordBias) &&
-         (unsigned) (b.z + kCoordBias) < (2u * kCoordBias);
-}
-__device__ __forceinline__ unsigned long long pack_key(i3 b) {
-  return ((unsigned long long) (unsigned) (b.x + kCoordBias) << 42) | ((unsigned long long) (unsigned) (b.y + kCoordBias) << 21) |
-         (unsigned long long) (unsigned) (b.z + kCoordBias);
-}
-__device__ __forceinline__ i3 unpack_key(unsigned long long k) {
-  return {(int) ((k >> 42) & 0x1FFFFF) - kCoordBias, (int) ((k >> 21) & 0x1FFFFF) - kCoordBias, (int) (k & 0x1FFFFF) - kCoordBias};
-}
-__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ void load_pose(const FrameDev& f, PoseDev& pose) {
-  for (int i = 0; i < 9; ++i)
-    pose.R[i] = f.R[i];
-  for (int i = 0; i < 3; ++i)
-    pose.t[i] = f.t[i];
-  pose_finish(pose);
-}
-
-// Single-thread lookup. Probe order: windows of two buckets starting at the home bucket; a window
-// that holds an EMPTY slot terminates the chain (inserts always take the first free slot in this
-// order and slots never return to EMPTY, so a present key sits before the first EMPTY).
-__device__ __forceinline__ int table_find(const MapDev& m, i3 b) {
-  if (!key_in_range(b))
-    return -1;
-  const unsigned long long key = pack_key(b);
-  const uint32_t h             = block_hash(b, m.num_buckets);
-#pragma unroll 1
-  for (int w = 0; w < kMaxWindows; ++w) {
-    bool has_empty = false;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const uint32_t bkt       = (h + 2u * w + half) % m.num_buckets;
-      const ulonglong2* row    = reinterpret_cast<const ulonglong2*>(m.keys + (size_t) bkt * kBucketSlots);
-#pragma unroll
-      for (int i = 0; i < kBucketSlots / 2; ++i) {
-        const ulonglong2 k2 = row[i];
-        if (k2.x == key)
-          return (int) (bkt * kBucketSlots + 2 * i);
-        if (k2.y == key)
-          return (int) (bkt * kBucketSlots + 2 * i + 1);
-        has_empty |= (k2.x == kEmpty) | (k2.y == kEmpty);
-      }
-    }
-    if (has_empty)
-      return -1;
-  }
-  return -1;
-}
-
-// Warp-cooperative "insert if absent and in the enlarged frustum" of one block key.
-// All 32 lanes call this with the same b. Lane l inspects slot l of the current 32-slot window
-// (one 256-byte coalesced read), the match is resolved with ballots, the frustum test of a new
-// block is spread over lanes 0..7 (one corner each) and lane 0 claims the slot with one 64-bit CAS
-// on the key word: claim and key publication are a single atomic, so two warps racing on the same
-// key can never both insert it and no bucket mutex / host retry loop is needed.
-template <bool FRUSTUM_TEST>
-__device__ __forceinline__ void warp_insert(const MapDev& m, const CameraDev& cam, const PoseDev& pose, uint32_t live_cur, i3 b, int lane) {
-  const unsigned full = 0xFFFFFFFFu;
-  if (!key_in_range(b)) {
-    if (lane == 0)
-      atomicAdd(&m.ctr->dropped_table, 1ull);
-    return;
-  }
-  const uint32_t h = block_hash(b, m.num_buckets);
-  if (h < m.shard_lo || h >= m.shard_hi)
-    return; // another GPU owns this bucket range
-  const unsigned long long key = pack_key(b);
-  bool frustum_ok              = !FRUSTUM_TEST;
-#pragma unroll 1
-  for (int attempt = 0; attempt < 1024; ++attempt) {
-    int free_slot                   = -1;
-    unsigned long long free_expected = kEmpty;
-    bool found = false, end = false;
-#pragma unroll 1
-    for (int w = 0; w < kMaxWindows && !end; ++w) {
-      const uint32_t bkt  = (h + 2u * w + (lane >> 4)) % m.num_buckets;
-      const uint32_t slot = bkt * kBucketSlots + (lane & 15);
-      const unsigned long long k = attempt == 0 ? m.keys[slot] : ld_cg_u64(m.keys + slot);
-      if (__ballot_sync(full, k == key)) {
-        found = true;
-        break;
-      }
-      const unsigned fr = __ballot_sync(full, k == kEmpty || k == kTomb);
-      const unsigned em = __ballot_sync(full, k == kEmpty);
-      if (free_slot < 0 && fr) {
-        const int src  = __ffs(fr) - 1;
-        free_slot      = (int) __shfl_sync(full, slot, src);
-        free_expected  = __shfl_sync(full, k, src);
-      }
-      end = em != 0;
-    }
-    if (found)
-      return;
-    if (free_slot < 0) {
-      if (lane == 0)
-        atomicAdd(&m.ctr->dropped_table, 1ull);
-      return;
-    }
-    if (!frustum_ok) {
-      const bool in = lane < 8 && block_corner_in_frustum(cam, pose, b, lane, m.voxel_size);
-      if (!__ballot_sync(full, in))
-        return;
-      frustum_ok = true;
-    }
-    unsigned long long prev = 0;
-    if (lane == 0)
-      prev = atomicCAS(m.keys + free_slot, free_expected, key);
-    prev = __shfl_sync(full, prev, 0);
-    if (prev == free_expected) {
-      if (lane == 0) {
-        const int addr = atomicSub(&m.ctr->heap_counter, 1); // consumeHeapHigh (:33-40)
-        if (addr < 0) {
-          atomicAdd(&m.ctr->heap_counter, 1);
-          atomicExch(m.keys + free_slot, kTomb);
-          atomicAdd(&m.ctr->dropped_heap, 1ull);
-        } else {
-          const uint32_t ptr = m.heap[addr];
-          m.vals[free_slot]  = ptr;
-          m.stats[ptr]       = {3.40282346638528859812e+38f, 0u};
-          const uint32_t cur = live_cur;
-          const uint32_t li  = atomicAdd(&m.ctr->live_count[cur], 1u);
-          m.live[cur][li]    = (uint32_t) free_slot;
-          atomicAdd(&m.ctr->blocks_new, 1ull);
-        }
-      }
-      return;
-    }
-    if (prev == key)
-      return; // another warp inserted the same key into the same slot first
-    // slot taken by a different key: rescan (reads now bypass L1)
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_alloc_rgbd: one thread per pixel, one warp per 32-pixel row segment.
@@ -639,67 +416,6 @@ __global__ void __launch_bounds__(128) k_gc_free(MapDev m, FrameDev f) {
       free_block(m, f.live_cur, e);
       m.stats[e.val] = {3.40282346638528859812e+38f, 0u};
       atomicAdd(&m.ctr->blocks_freed, 1ull);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_gather_blocks: live list -> dense (record, AoS payload) buffers for streamAllOut /
-// serializeData / the parity dump (replaces the Streamer's integrateFromGlobalHashPass1/2,
-// streamer.cu:77-187: no per-thread serial prefix sums).
-// ---------------------------------------------------------------------------------------------
-struct GatherRecord {
-  int x, y, z, resolution, ptr;
-};
-
-__global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_cur, GatherRecord* records, uint32_t* voxels_aos, uint32_t* out_count, uint32_t max_out) {
-  __shared__ uint32_t s_out;
-  const int tid    = threadIdx.x;
-  const uint32_t n = m.ctr->live_count[live_cur];
-  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t slot = m.live[live_cur][i];
-    if (slot == kInvalid)
-      continue;
-    const unsigned long long key = m.keys[slot];
-    if (key >= kNoKey)
-      continue;
-    const uint32_t val = m.vals[slot];
-    if (tid == 0)
-      s_out = atomicAdd(out_count, 1u);
-    __syncthreads();
-    const uint32_t o = s_out;
-    __syncthreads();
-    if (o >= max_out)
-      continue;
-    const i3 b = unpack_key(key);
-    if (tid == 0)
-      records[o] = {b.x, b.y, b.z, (int) (val >> 31), (int) ((val & 0x7FFFFFFFu) * ((val >> 31) ? 64u : 512u))};
-    uint32_t* dst = voxels_aos + (size_t) o * kBlockVoxels * 3;
-    if (!(val >> 31)) {
-      const uint8_t* base = m.pool + (size_t) val * kBlockBytes;
-      const float4 sdf4   = reinterpret_cast<const float4*>(base)[tid];
-      const float4 ss4    = reinterpret_cast<const float4*>(base + kPlaneBytes)[tid];
-      const uint4 cw4     = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
-      const float sv[4] = {sdf4.x, sdf4.y, sdf4.z, sdf4.w}, qv[4] = {ss4.x, ss4.y, ss4.z, ss4.w};
-      const uint32_t cv[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        dst[(tid * 4 + j) * 3 + 0] = __float_as_uint(sv[j]);
-        dst[(tid * 4 + j) * 3 + 1] = __float_as_uint(qv[j]);
-        dst[(tid * 4 + j) * 3 + 2] = cv[j];
-      }
-    } else {
-      // resolution 1: 64 voxels in a 768-byte sub-slot laid out as sdf[64] | sum_sq[64] | rgbw[64]
-      const uint8_t* base = m.pool + (size_t) (val & 0x7FFFFFFFu) * 768u;
-      for (int v = tid; v < kBlockVoxels; v += 128) {
-        uint32_t a = 0, b2 = 0, c = 0;
-        if (v < 64) {
-          a  = reinterpret_cast<const uint32_t*>(base)[v];
-          b2 = reinterpret_cast<const uint32_t*>(base + 256)[v];
-          c  = reinterpret_cast<const uint32_t*>(base + 512)[v];
-        }
-        dst[v * 3 + 0] = a, dst[v * 3 + 1] = b2, dst[v * 3 + 2] = c;
-      }
     }
   }
 }

@@ -1,0 +1,122 @@
+// mrh_types.cuh — device-visible data structures of the map (shared by every translation unit).
+//
+// Data layout in HBM:
+//   keys[capacity] u64   packed block position (21 bits/axis, biased), EMPTY / TOMB sentinels;
+//                        bucket = 16 consecutive keys = one 128-byte line, bucket index =
+//                        calculateHash(pos) of the reference (voxel_data_structures.cu:151-160)
+//   vals[capacity] u32   pool block index (bit 31 = resolution 1, then index is a 64-voxel sub-slot)
+//   pool[num_blocks]     6144 B per block as three 2 KB planes: f32 sdf[512] | f32 sum_sq[512] |
+//                        u32 rgbw[512] (r | g<<8 | b<<16 | weight<<24) -> 128-bit coalesced access.
+//                        A block carved for resolution 1 holds 8 sub-slots of 768 B, each
+//                        sdf[64] | sum_sq[64] | rgbw[64].
+//   stats[num_blocks]    per pool block {min |sdf| over weight>0, max weight}: the GC predicate of
+//                        untouched blocks is answered without re-reading their payload
+//   heap[num_blocks]     free stack of pool indices (heap[i] = N-1-i initially, voxel_data_structures.cpp:58-69)
+//   heap_low[8*num_blocks] free stack of 64-voxel sub-slot indices (allocateMemoryLow :860-871)
+//   live[2][2*num_blocks] dense list of occupied table slots (double buffered, compacted per frame)
+//   vis[2*num_blocks]    per-frame list of in-frustum blocks (the reference's compact hash table)
+#pragma once
+#include "mrh_math.cuh"
+
+namespace mrh {
+
+constexpr unsigned long long kEmpty   = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned long long kTomb    = 0xFFFFFFFFFFFFFFFEull;
+constexpr unsigned long long kNoKey   = 0xFFFFFFFFFFFFFFFDull;
+constexpr uint32_t kInvalid           = 0xFFFFFFFFu;
+constexpr int kBucketSlots            = 16;
+constexpr int kMaxWindows             = 64; // 2 buckets per window
+constexpr uint32_t kBlockBytes        = 6144;
+constexpr uint32_t kPlaneBytes        = 2048;
+constexpr int kCoordBias              = 1 << 20;
+
+struct Counters {
+  int heap_counter;      // index of the stack top; free = heap_counter + 1 (voxel_data_structures.cpp:148-153)
+  int heap_low_counter;
+  uint32_t live_count[2];
+  uint32_t vis_count;
+  uint32_t n_realloc;
+  uint32_t n_reintegrate;
+  uint32_t pad0;
+  // per-run totals (read back on demand)
+  unsigned long long rays_valid;
+  unsigned long long blocks_new;
+  unsigned long long blocks_visible;
+  unsigned long long voxels_updated;
+  unsigned long long blocks_freed;
+  unsigned long long blocks_realloc;
+  unsigned long long dropped_heap;   // allocBlock "mem size exceed" events
+  unsigned long long dropped_table;  // probe sequence exhausted / coordinate out of key range
+  // map state (not reset by mrh_reset_stats)
+  unsigned long long low_parents;    // pool blocks carved into 64-voxel sub-slots
+  unsigned long long low_live;       // live resolution-1 blocks
+};
+
+struct BlockStats {
+  float min_abs_sdf; // FLT_MAX when no voxel has weight > 0
+  uint32_t max_weight;
+};
+
+struct __align__(16) VisEntry {
+  int x, y, z;
+  uint32_t val;
+  uint32_t slot;
+  uint32_t live_idx;
+  uint32_t pad0, pad1;
+};
+
+// record of a gathered block (same layout as mrh_dump_entry)
+struct GatherRecord {
+  int x, y, z, resolution, ptr;
+};
+
+struct FrameDev {
+  float R[9];
+  float t[3];
+  uint32_t frame_index;
+  uint32_t live_cur; // which live list is the input of this frame
+  uint32_t pad[2];
+};
+
+struct MapDev {
+  float voxel_size, trunc, trunc_scale, max_integration_distance;
+  float ext[3];
+  float gc_threshold; // host: trunc + scale * camera.maxDepth() (voxel_data_structures.cu:1720)
+  float var_threshold;
+  float mc_threshold;
+  int weight_sample;
+  int min_weight_threshold;
+  int projective;
+  uint32_t num_buckets, capacity, num_blocks;
+  uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
+  unsigned long long* keys;
+  uint32_t* vals;
+  uint32_t* heap;
+  uint32_t* heap_low;
+  uint8_t* pool;
+  BlockStats* stats;
+  uint32_t* live[2];
+  VisEntry* vis;
+  VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
+  unsigned long long* zbuf;
+  Counters* ctr;
+};
+
+__device__ __forceinline__ bool key_in_range(i3 b) {
+  return (unsigned) (b.x + kCoordBias) < (2u * kCoordBias) && (unsigned) (b.y + kCoordBias) < (2u * kCoordBias) &&
+         (unsigned) (b.z + kCoordBias) < (2u * kCoordBias);
+}
+__device__ __forceinline__ unsigned long long pack_key(i3 b) {
+  return ((unsigned long long) (unsigned) (b.x + kCoordBias) << 42) | ((unsigned long long) (unsigned) (b.y + kCoordBias) << 21) |
+         (unsigned long long) (unsigned) (b.z + kCoordBias);
+}
+__device__ __forceinline__ i3 unpack_key(unsigned long long k) {
+  return {(int) ((k >> 42) & 0x1FFFFF) - kCoordBias, (int) ((k >> 21) & 0x1FFFFF) - kCoordBias, (int) (k & 0x1FFFFF) - kCoordBias};
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+} // namespace mrh
