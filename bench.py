@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""bench.py — RGB-D frames/s (and Mvoxels-updated/s, % of HBM roofline) of the compute() hot path.
+
+Workload (BASELINE.json configs[1]): synthetic 640x480 orbiting-camera RGB-D stream (scene S2 of
+SURVEY.md §8d, replica.cfg parameters), one "step" = one frame through compute(): block
+allocation -> visibility -> TSDF fusion + garbage collection.
+
+  value  : frames/s with the frames already resident in HBM (device pointers handed to the C ABI),
+           L2 flushed before every step, per-step CUDA-event time summed, max over ranks.
+  e2e    : frames/s through the public GeoWrapper API with HOST buffers: per step setCurrPose +
+           setDepthImage + setRGBImage (pinned staging + H2D) + compute() + getStats() (D2H read).
+  roofline: the dominant kernel, algorithmic bytes / CUDA-event kernel time vs MEASURED_PEAKS.json.
+  cpu_baseline: the CPU restatement (oracle/) with OpenMP on the host cores, bounded sample.
+
+`--impl reference` runs the UNMODIFIED reference kernels (oracle/_ref/libref_harness.so, compiled
+from /root/reference for sm_100a) on the same stream, host buffers in, the way GeoWrapper::compute
+drives them. N>1 (torchrun): the map is sharded by hash-bucket range, rank 0 ingests each frame and
+broadcasts it over NCCL; every rank allocates / fuses only the blocks it owns.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
+HASH_NUM_BUCKETS = 250000
+L2_FLUSH_BYTES = 256 << 20
+COUNTERS_BYTES = 112  # sizeof(mrh::Counters)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--orbit-frames", type=int, default=1000, help="frames per full orbit of scene S2")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed regions (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL,
+                text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, r in self.rows:
+            if len(r) < 8 or not any(a <= ts <= b for a, b in windows):
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_stream(args, n, device):
+    """Frames 0..n-1 of scene S2 rendered on `device` (torch), plus poses."""
+    import torch
+
+    from mrhash_b200 import synth
+
+    depth = torch.empty((n, args.height, args.width), dtype=torch.float32, device=device)
+    rgb = torch.empty((n, args.height, args.width, 3), dtype=torch.uint8, device=device)
+    poses = []
+    for k in range(n):
+        t, q, R = synth.orbit_pose(k, args.orbit_frames)
+        d, c = synth.render_rgbd_torch(R, t, args.width, args.height, device=device)
+        depth[k], rgb[k] = d, c
+        poses.append((t, q))
+    return depth, rgb, poses
+
+
+def new_map(args, rank, world, device_index):
+    from mrhash_b200 import GeoWrapper, synth
+
+    p = dict(synth.REPLICA_PARAMS)
+    g = GeoWrapper(**p, num_sdf_blocks=NUM_SDF_BLOCKS, hash_num_buckets=HASH_NUM_BUCKETS, max_num_triangles=1, device=device_index, shard_rank=rank, shard_world=world)
+    fx, fy, cx, cy = synth.intrinsics(args.width, args.height)
+    g.setCamera(fx, fy, cx, cy, args.height, args.width, p["min_depth"], p["max_depth"], 0)
+    return g
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(args, depth_h, rgb_h, poses, budget_s):
+    """The CPU restatement with all host threads on the first frames of the same stream."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+
+    from mrhash_b200 import synth
+
+    cores = len(os.sched_getaffinity(0))
+    p = dict(synth.REPLICA_PARAMS)
+    o = Oracle(p, 100000, 50000, threads=cores)
+    fx, fy, cx, cy = synth.intrinsics(args.width, args.height)
+    o.set_camera(fx, fy, cx, cy, args.height, args.width, p["min_depth"], p["max_depth"], 0)
+    t0 = time.perf_counter()
+    n = 0
+    while n < len(poses) and (time.perf_counter() - t0 < budget_s or n < 3):
+        t, q = poses[n]
+        o.compute_rgbd(synth.quat_to_matrix_f32(t, q), depth_h[n], rgb_h[n])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"first {n} frames of the same {args.width}x{args.height} stream ({dt:.1f} s), oracle/mrh_oracle.c with OpenMP over pixel rows / blocks"}
+
+
+def run_reference(args, rank, world):
+    """The reference's own kernels (oracle/_ref), driven like GeoWrapper::compute, host buffers in."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    from oracle_lib import RefCuda, ref_available
+
+    from mrhash_b200 import synth
+
+    base = {"impl": "reference", "metric": "rgbd_frames_per_sec", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True}
+    if not ref_available() or not torch.cuda.is_available():
+        print(json.dumps({**base, "unavailable": "oracle/_ref/libref_harness.so missing or no CUDA device"}))
+        return
+    n = args.warmup + args.steps
+    depth, rgb, poses = make_stream(args, n, "cuda:0")
+    depth_h, rgb_h = depth.cpu().numpy(), rgb.cpu().numpy()
+    del depth, rgb
+    p = dict(synth.REPLICA_PARAMS)
+    fx, fy, cx, cy = synth.intrinsics(args.width, args.height)
+    # silence the reference's per-frame prints (stdout of this process must stay one JSON line)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1), os.dup(2)
+    os.dup2(devnull, 1), os.dup2(devnull, 2)
+    try:
+        cwd = os.getcwd()
+        os.makedirs("/tmp/mrh_ref_run", exist_ok=True)
+        os.chdir("/tmp/mrh_ref_run")  # the reference writes ./<name>.txt profiler logs
+        r = RefCuda(p, NUM_SDF_BLOCKS, HASH_NUM_BUCKETS)
+        r.set_camera(fx, fy, cx, cy, args.height, args.width, p["min_depth"], p["max_depth"], 0)
+        sampler = ClockSampler(0)
+        sampler.start()
+        for k in range(args.warmup):
+            r.compute_rgbd(synth.quat_to_matrix_f32(*poses[k]), depth_h[k], rgb_h[k])
+        torch.cuda.synchronize()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        integ_ms = 0.0
+        for k in range(args.warmup, n):
+            r.compute_rgbd(synth.quat_to_matrix_f32(*poses[k]), depth_h[k], rgb_h[k])
+            integ_ms += r.last_integrate_ms()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        w1 = time.time()
+        sampler.stop()
+        occupied = r.occupied()
+        os.chdir(cwd)
+    finally:
+        os.dup2(saved[0], 1), os.dup2(saved[1], 2)
+    fps = args.steps / dt
+    line = {
+        **base,
+        "value": fps,
+        "ms_per_step": 1e3 * dt / args.steps,
+        "scaling": "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"S2 orbiting-camera RGB-D stream {args.width}x{args.height}, replica.cfg parameters", "num_sdf_blocks": NUM_SDF_BLOCKS, "hash_num_buckets": HASH_NUM_BUCKETS, "l2": "not flushed (host-driven, synchronous reference)"},
+        "integrate_only_fps": args.steps / (integ_ms * 1e-3) if integ_ms > 0 else None,
+        "visible_blocks_last_frame": occupied,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "kind": "reference", "cores": 1, "sample": f"{args.steps} frames; the reference has no CPU path: this is its own CUDA code (oracle/_ref, -arch=sm_100a) driven by one host thread"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "clocks": sampler.summary([(w0, w1)]),
+        "gpu_launches": None,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (mrhash_b200 has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sum_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return x
+
+    W, K = args.warmup, args.steps
+    n = W + K
+    depth, rgb, poses = make_stream(args, n, dev)
+    P = args.width * args.height
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+
+    # ---------------- pass A: device-resident inputs, L2 flushed before every step -----------------
+    g = new_map(args, rank, world, local)
+    stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
+
+    def step_device(k):
+        g.setCurrPose(*poses[k])
+        g.setDepthImageDevice(depth[k].data_ptr(), args.height, args.width)
+        g.setRGBImageDevice(rgb[k].data_ptr(), args.height, args.width)
+        g.compute()
+
+    for k in range(W):
+        step_device(k)
+    g.synchronize()
+    g.resetStats()
+    launches0 = g.launchCount()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    windows.append([time.time(), None])
+    with torch.cuda.stream(stream):
+        for i in range(K):
+            flush.zero_()
+            ev[i][0].record(stream)
+            step_device(W + i)
+            ev[i][1].record(stream)
+    g.synchronize()
+    barrier()
+    windows[-1][1] = time.time()
+    ms_flushed = sum(a.elapsed_time(b) for a, b in ev)
+    ms_flushed = max_over_ranks(ms_flushed)
+    st = g.getStats()
+    launches = g.launchCount() - launches0
+    v_upd = sum_over_ranks(st["voxels_updated"])
+    b_vis = sum_over_ranks(st["blocks_visible"])
+    b_new = sum_over_ranks(st["blocks_new"])
+    live = sum_over_ranks(st["live_blocks"])
+    assert st["dropped_heap"] == 0 and st["dropped_table"] == 0, st
+    g.close()
+
+    # ---------------- pass A': same, L2 as the stream leaves it (whole region, one event pair) -------
+    g = new_map(args, rank, world, local)
+    stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
+    for k in range(W):
+        step_device(k)
+    g.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    windows.append([time.time(), None])
+    e0.record(stream)
+    for i in range(K):
+        step_device(W + i)
+    e1.record(stream)
+    g.synchronize()
+    barrier()
+    windows[-1][1] = time.time()
+    ms_stream = max_over_ranks(e0.elapsed_time(e1))
+    g.close()
+
+    # ---------------- pass B: end to end through the public API, host buffers ----------------------
+    depth_h = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
+    rgb_h = torch.empty(rgb.shape, dtype=rgb.dtype, pin_memory=True)
+    depth_h.copy_(depth)
+    rgb_h.copy_(rgb)
+    depth_np, rgb_np = depth_h.numpy(), rgb_h.numpy()
+    g = new_map(args, rank, world, local)
+    stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
+    bcast_d = torch.empty((args.height, args.width), dtype=torch.float32, device=dev) if world > 1 else None
+    bcast_c = torch.empty((args.height, args.width, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+
+    def step_host(k):
+        g.setCurrPose(*poses[k])
+        if world == 1:
+            g.setDepthImage(depth_np[k])
+            g.setRGBImage(rgb_np[k])
+        else:
+            # rank 0 ingests the frame from its host buffers; the others receive it over NVLink
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    bcast_d.copy_(depth_h[k], non_blocking=True)
+                    bcast_c.copy_(rgb_h[k], non_blocking=True)
+                dist.broadcast(bcast_d, 0)
+                dist.broadcast(bcast_c, 0)
+            g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
+            g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
+        g.compute()
+        return g.getStats()  # D2H read of the frame's counters (synchronises)
+
+    for k in range(W):
+        step_host(k)
+    barrier()
+    windows.append([time.time(), None])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for i in range(K):
+        step_host(W + i)
+    e1.record(stream)
+    g.synchronize()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    windows[-1][1] = time.time()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_e2e * 1e3))
+    g.close()
+
+    # ---------------- roofline pass: per-kernel CUDA-event times, L2 flushed ------------------------
+    Kp = min(K, 200)
+    g = new_map(args, rank, world, local)
+    stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
+    for k in range(W):
+        step_device(k)
+    g.synchronize()
+    g.resetStats()
+    g.setProfiling(True)
+    with torch.cuda.stream(stream):
+        for i in range(Kp):
+            flush.zero_()
+            step_device(W + i)
+    g.synchronize()
+    kms, kn = g.kernelTimes()
+    stp = g.getStats()
+    g.setProfiling(False)
+    g.close()
+    sampler.stop()
+
+    peak, peak_src = peaks()
+    names = ["k_alloc_rgbd", "k_visible", "k_integrate"]
+    per_kernel = {names[i]: {"ms_per_launch": kms[i] / max(kn[i], 1), "launches": kn[i]} for i in range(3)}
+    # algorithmic bytes per launch: integrate = 24 B per updated voxel (12 read + 12
+    # written) + 32 B per visible block record + 7 B per pixel (depth + rgb read once)
+    bytes_integrate = (24.0 * stp["voxels_updated"] + 32.0 * stp["blocks_visible"]) / Kp + 7.0 * P
+    bytes_alloc = 4.0 * P + 8.0 * 16 * stp["blocks_new"] / Kp  # depth read once + one bucket row per new block
+    bytes_visible = (4.0 + 8.0 + 4.0) * stp["live_blocks"] + 32.0 * stp["blocks_visible"] / Kp
+    algo = {"k_integrate": bytes_integrate, "k_alloc_rgbd": bytes_alloc, "k_visible": bytes_visible}
+    dom = max(names, key=lambda k: per_kernel[k]["ms_per_launch"])
+    achieved = algo[dom] / (per_kernel[dom]["ms_per_launch"] * 1e-3) / 1e9 if per_kernel[dom]["ms_per_launch"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(args, depth_np, rgb_np, poses, args.cpu_seconds)
+        fps = K / (ms_flushed * 1e-3)
+        line = {
+            "metric": "rgbd_frames_per_sec",
+            "value": fps,
+            "unit": "frames/s",
+            "n_gpus": world,
+            "steps": K,
+            "warmup": W,
+            "ms_per_step": ms_flushed / K,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"S2 orbiting-camera RGB-D stream {args.width}x{args.height} ({args.orbit_frames} frames/orbit), replica.cfg parameters (BASELINE configs[1])",
+                "num_sdf_blocks": NUM_SDF_BLOCKS,
+                "hash_num_buckets": HASH_NUM_BUCKETS,
+                "l2": "flushed before every step (256 MiB memset, excluded from the per-step CUDA-event window)",
+                "parallelism": "1 GPU" if world == 1 else f"map sharded by hash-bucket range over {world} GPUs, frame broadcast over NCCL",
+            },
+            "mvoxels_updated_per_sec": v_upd / (ms_flushed * 1e-3) / 1e6,
+            "voxels_updated_per_frame": v_upd / K,
+            "visible_blocks_per_frame": b_vis / K,
+            "new_blocks_per_frame": b_new / K,
+            "live_blocks_end": live,
+            "stream_fps_l2_warm": K / (ms_stream * 1e-3),
+            "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
+            "kernels": per_kernel,
+            "frame_algorithmic_bytes": 7.0 * P + (24.0 * (b_vis + b_new) + 24.0 * v_upd) / K,
+            "clocks": sampler.summary([tuple(w) for w in windows]),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

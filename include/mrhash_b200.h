@@ -135,6 +135,11 @@ int mrh_get_stats(mrh_map* m, mrh_stats* out);
 int mrh_reset_stats(mrh_map* m);
 /* device time of the last compute() in ms (CUDAProfiler::CUDAEvent window, voxel_data_structures.cpp:94-109); synchronises */
 int mrh_last_compute_ms(mrh_map* m, float* ms);
+/* Per-kernel device timing for the roofline pass of bench.py: when enabled, compute() records CUDA
+ * events between its kernels and waits for the frame, accumulating ms per kernel slot
+ * (RGB-D: 0 = allocate, 1 = visibility, 2 = integrate[+GC]). Enabling resets the accumulators. */
+int mrh_set_profiling(mrh_map* m, int enabled);
+int mrh_get_kernel_times(mrh_map* m, double ms_out[8], uint64_t launches_out[8]);
 /* the CUDA stream compute() runs on (cudaStream_t), for event timing by the caller */
 int mrh_get_stream(mrh_map* m, void** stream);
 /* number of kernel launches issued by this handle so far */

@@ -99,6 +99,8 @@ SIGNATURES = {
     "mrh_get_stats": ([_vp, _P(Stats)], _i),
     "mrh_reset_stats": ([_vp], _i),
     "mrh_last_compute_ms": ([_vp, _fp], _i),
+    "mrh_set_profiling": ([_vp, _i], _i),
+    "mrh_get_kernel_times": ([_vp, _P(C.c_double), _P(C.c_uint64)], _i),
     "mrh_get_stream": ([_vp, _P(_vp)], _i),
     "mrh_get_launch_count": ([_vp, _P(C.c_uint64)], _i),
     "mrh_dump_state": ([_vp, _vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),

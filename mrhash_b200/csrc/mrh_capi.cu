@@ -118,6 +118,9 @@ static void free_map(mrh_map* m) {
   }
   cudaFree(m->d_tri), cudaFree(m->d_tri_count);
   cudaFreeHost(m->h_ctr);
+  for (int i = 0; i < 8; ++i)
+    if (m->ev_k[i])
+      cudaEventDestroy(m->ev_k[i]);
   if (m->ev0)
     cudaEventDestroy(m->ev0);
   if (m->ev1)
@@ -230,6 +233,8 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
     CK(cudaEventCreateWithFlags(&m->ev_points[i], cudaEventDisableTiming));
   }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
+  for (int i = 0; i < 8; ++i)
+    CK(cudaEventCreate(&m->ev_k[i]));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   m->num_sms = prop.multiProcessorCount;
@@ -534,6 +539,23 @@ int mrh_last_compute_ms(mrh_map* m, float* ms) {
     return fail("null argument");
   CK(cudaEventSynchronize(m->ev1));
   CK(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+  return 0;
+}
+
+int mrh_set_profiling(mrh_map* m, int enabled) {
+  GUARD(m);
+  CK(cudaStreamSynchronize(m->stream));
+  m->profiling = enabled != 0;
+  for (int i = 0; i < 8; ++i)
+    m->kernel_ms[i] = 0.0, m->kernel_launches[i] = 0;
+  return 0;
+}
+
+int mrh_get_kernel_times(mrh_map* m, double ms_out[8], uint64_t launches_out[8]) {
+  if (!m || !ms_out || !launches_out)
+    return fail("null argument");
+  for (int i = 0; i < 8; ++i)
+    ms_out[i] = m->kernel_ms[i], launches_out[i] = m->kernel_launches[i];
   return 0;
 }
 

@@ -41,20 +41,30 @@ int integrate_rgbd(mrh_map* m) {
   if (var)
     return fail("sdf_var_threshold > 0 is not wired up yet");
 
+  const bool prof = m->profiling;
+  auto mark = [&](int i) {
+    if (prof)
+      cudaEventRecord(m->ev_k[i], s);
+  };
   const dim3 grid_alloc((c.cols + 31) / 32, (c.rows + 7) / 8);
+  mark(0);
   k_alloc_rgbd<<<grid_alloc, 256, 0, s>>>(d, f, c, m->depth_ptr);
   CKL();
+  mark(1);
   k_visible<<<m->num_sms * 4, 256, 0, s>>>(d, f, c, 1);
   CKL();
+  mark(2);
   m->launches += 2;
   const int grid_blocks = m->num_sms * 8;
   if (gc && !starve) {
     k_integrate<true><<<grid_blocks, 128, 0, s>>>(d, f, c, m->depth_ptr, m->rgb_ptr);
     CKL();
+    mark(3);
     m->launches += 1;
   } else {
     k_integrate<false><<<grid_blocks, 128, 0, s>>>(d, f, c, m->depth_ptr, m->rgb_ptr);
     CKL();
+    mark(3);
     m->launches += 1;
     if (starve) {
       if (cudaMemsetAsync(d.zbuf, 0xFF, sizeof(unsigned long long) * c.rows * c.cols, s) != cudaSuccess)
@@ -65,6 +75,17 @@ int integrate_rgbd(mrh_map* m) {
       k_gc_free<<<grid_blocks, 128, 0, s>>>(d, f);
       CKL();
       m->launches += 4;
+    }
+  }
+  if (prof) {
+    // profiling pass only: wait for the frame and accumulate the per-kernel device times
+    if (cudaEventSynchronize(m->ev_k[3]) != cudaSuccess)
+      return fail("profiling: event synchronize failed");
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, m->ev_k[i], m->ev_k[i + 1]);
+      m->kernel_ms[i] += ms;
+      m->kernel_launches[i] += 1;
     }
   }
   m->live_cur ^= 1u;

@@ -85,6 +85,12 @@ struct mrh_map {
   uint64_t h2d_bytes    = 0;
   mrh::Counters* h_ctr  = nullptr; // pinned read-back
 
+  // optional per-kernel timing (bench.py roofline pass): events between the kernels of a frame
+  bool profiling = false;
+  cudaEvent_t ev_k[8]{};
+  double kernel_ms[8]{};
+  uint64_t kernel_launches[8]{};
+
   // meshing
   float* d_tri           = nullptr;
   size_t d_tri_cap       = 0;

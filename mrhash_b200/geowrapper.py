@@ -336,6 +336,16 @@ class GeoWrapper:
         check(self._lib.mrh_get_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def setProfiling(self, enabled):
+        check(self._lib.mrh_set_profiling(self._h, int(bool(enabled))))
+
+    def kernelTimes(self):
+        """({slot: total ms}, {slot: launches}) accumulated since setProfiling(True)."""
+        ms = (C.c_double * 8)()
+        n = (C.c_uint64 * 8)()
+        check(self._lib.mrh_get_kernel_times(self._h, ms, n))
+        return list(ms), list(n)
+
     def cudaStream(self):
         s = C.c_void_p()
         check(self._lib.mrh_get_stream(self._h, C.byref(s)))

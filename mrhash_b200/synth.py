@@ -180,3 +180,40 @@ def lidar_frame(k=0, rows=LIDAR_ROWS, cols=LIDAR_COLS, seed=2, noise_sigma=0.0):
     T = np.eye(4, dtype=np.float32)
     T[:3, 3] = o.astype(np.float32)
     return T, pts
+
+
+def render_rgbd_torch(R, t, width=640, height=480, device="cuda"):
+    """Same ray-cast as render_rgbd, evaluated with torch on `device` (bench.py generates its
+    1000+ frame stream this way). Returns (depth f32 [H,W], rgb u8 [H,W,3]) tensors on `device`."""
+    import torch
+
+    f64 = torch.float64
+    fx, fy, cx, cy = intrinsics(width, height)
+    cols = torch.arange(width, dtype=f64, device=device)[None, :].expand(height, width)
+    rows = torch.arange(height, dtype=f64, device=device)[:, None].expand(height, width)
+    d_cam = torch.stack([(cols - cx - 0.5) / fx, (rows - cy - 0.5) / fy, torch.ones_like(cols)], dim=-1)
+    Rt = torch.as_tensor(np.asarray(R, np.float64), device=device)
+    d = d_cam @ Rt.T
+    o = torch.as_tensor(np.asarray(t, np.float64), device=device)
+    lo = torch.as_tensor(ROOM_MIN, device=device)
+    hi = torch.as_tensor(ROOM_MAX, device=device)
+    inf = torch.full_like(d, float("inf"))
+    t_hi = torch.where(d > 0, (hi - o) / d, torch.where(d < 0, (lo - o) / d, inf))
+    t_box = t_hi.min(dim=-1).values
+    oc = o - torch.as_tensor(SPHERE_C, device=device)
+    a = (d * d).sum(-1)
+    b = 2.0 * (d * oc).sum(-1)
+    c = (oc * oc).sum() - SPHERE_R**2
+    disc = b * b - 4 * a * c
+    t_sph = torch.where(disc > 0, (-b - torch.sqrt(disc.clamp_min(0))) / (2 * a), torch.full_like(a, float("inf")))
+    t_sph = torch.where(t_sph > 1e-6, t_sph, torch.full_like(a, float("inf")))
+    depth = torch.minimum(t_box, t_sph)
+    hit = o + depth[..., None] * d
+    q = torch.floor(hit * 16.0).to(torch.int64)
+    h = ((q[..., 0] * 73856093) ^ (q[..., 1] * 19349669) ^ (q[..., 2] * 83492791)) & 0xFFFFFFFF
+    h = h ^ (h >> 13)
+    h = (h * 0x5BD1E995) & 0xFFFFFFFF
+    h = h ^ (h >> 15)
+    rgb = torch.stack([h & 0xFF, (h >> 8) & 0xFF, (h >> 16) & 0xFF], dim=-1).to(torch.uint8)
+    depth = torch.round(depth * DEPTH_SCALE) / DEPTH_SCALE
+    return depth.to(torch.float32).contiguous(), rgb.contiguous()
