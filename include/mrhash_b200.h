@@ -118,6 +118,8 @@ int mrh_stream_all_out(mrh_map* m);
 int mrh_store_size(mrh_map* m, size_t* n_blocks);
 /* GeoWrapper::extractMesh (geowrapper.cpp:150-230): marching cubes + host weld + ASCII PLY (path may be NULL: no file) */
 int mrh_extract_mesh(mrh_map* m, const char* path_or_null);
+/* same; force_generic != 0 sends every block through the per-read hash sampler (test / validation of the shared-memory path) */
+int mrh_extract_mesh_ex(mrh_map* m, const char* path_or_null, int force_generic);
 /* GeoWrapper::getVertices / getFaces / getColors (geowrapper.h:91-93); pointers stay valid until the next extract */
 int mrh_get_mesh(mrh_map* m, const double** vertices, const int32_t** faces, const double** colors, size_t* n_vertices, size_t* n_faces);
 /* raw triangle soup of the last extract (72-byte Triangle records, voxel_hash_utils.cuh:46-64) */

@@ -90,6 +90,7 @@ SIGNATURES = {
     "mrh_stream_all_out": ([_vp], _i),
     "mrh_store_size": ([_vp, _P(C.c_size_t)], _i),
     "mrh_extract_mesh": ([_vp, C.c_char_p], _i),
+    "mrh_extract_mesh_ex": ([_vp, C.c_char_p, _i], _i),
     "mrh_get_mesh": ([_vp, _P(_P(C.c_double)), _P(_P(C.c_int32)), _P(_P(C.c_double)), _P(C.c_size_t), _P(C.c_size_t)], _i),
     "mrh_get_triangles": ([_vp, _P(_fp), _P(C.c_size_t)], _i),
     "mrh_serialize_data": ([_vp, C.c_char_p, C.c_char_p], _i),

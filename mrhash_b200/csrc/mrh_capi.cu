@@ -80,6 +80,7 @@ static int alloc_map(mrh_map* m) {
   CK(cudaMalloc(&d.heap, sizeof(uint32_t) * N));
   CK(cudaMalloc(&d.heap_low, sizeof(uint32_t) * N * 8));
   CK(cudaMalloc(&d.pool, (size_t) kBlockBytes * N));
+  CK(cudaMalloc(&d.carved, N));
   CK(cudaMalloc(&d.stats, sizeof(BlockStats) * N));
   CK(cudaMalloc(&d.live[0], sizeof(uint32_t) * N * 2));
   CK(cudaMalloc(&d.live[1], sizeof(uint32_t) * N * 2));
@@ -94,6 +95,7 @@ int mrh::reset_map(mrh_map* m) {
   CK(cudaMemsetAsync(d.keys, 0xFF, sizeof(unsigned long long) * d.capacity, m->stream));
   CK(cudaMemsetAsync(d.vals, 0xFF, sizeof(uint32_t) * d.capacity, m->stream));
   CK(cudaMemsetAsync(d.pool, 0, (size_t) kBlockBytes * d.num_blocks, m->stream));
+  CK(cudaMemsetAsync(d.carved, 0, d.num_blocks, m->stream));
   k_init_heap<<<592, 256, 0, m->stream>>>(d.heap, d.stats, d.num_blocks);
   k_init_counters<<<1, 1, 0, m->stream>>>(d.ctr, d.num_blocks);
   m->launches += 2;
@@ -104,7 +106,7 @@ int mrh::reset_map(mrh_map* m) {
 
 static void free_map(mrh_map* m) {
   MapDev& d = m->dev;
-  cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.stats);
+  cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.carved), cudaFree(d.stats);
   cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.ctr), cudaFree(d.zbuf);
   cudaFree(m->d_depth), cudaFree(m->d_rgb), cudaFree(m->d_points);
   for (int i = 0; i < 2; ++i) {

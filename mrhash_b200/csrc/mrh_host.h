@@ -2,6 +2,8 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -28,11 +30,42 @@ namespace mrh {
     }
   };
 
+  struct VertexKey {
+    uint64_t a, b, c; // bit patterns of 3 doubles (exact merge) or 3 quantised ints
+    bool operator==(const VertexKey& o) const {
+      return a == o.a && b == o.b && c == o.c;
+    }
+  };
+  struct VertexKeyHash {
+    size_t operator()(const VertexKey& k) const {
+      uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
+      h ^= (k.b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+      h ^= (k.c + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+      return (size_t) h;
+    }
+  };
+  struct FaceKey {
+    int32_t a, b, c;
+    bool operator==(const FaceKey& o) const {
+      return a == o.a && b == o.b && c == o.c;
+    }
+  };
+  struct FaceKeyHash {
+    size_t operator()(const FaceKey& k) const {
+      return (size_t) (((uint64_t) (uint32_t) k.a * 73856093ull) ^ ((uint64_t) (uint32_t) k.b * 19349669ull << 1) ^ ((uint64_t) (uint32_t) k.c * 83492791ull << 2));
+    }
+  };
   struct HostMesh {
     std::vector<float> triangles; // raw soup of the last extraction, 18 floats per triangle
     std::vector<double> vertices; // V x 3
     std::vector<int32_t> faces;   // F x 3
     std::vector<double> colors;   // V x 3
+    std::unordered_map<VertexKey, int32_t, VertexKeyHash> vertex_map;
+    std::unordered_set<FaceKey, FaceKeyHash> face_set;
+    void clear() {
+      triangles.clear(), vertices.clear(), faces.clear(), colors.clear();
+      vertex_map.clear(), face_set.clear();
+    }
   };
 
   int fail(const char* fmt, ...);

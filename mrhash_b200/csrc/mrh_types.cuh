@@ -94,6 +94,7 @@ struct MapDev {
   uint32_t* heap;
   uint32_t* heap_low;
   uint8_t* pool;
+  uint8_t* carved; // 1 = pool block split into 8 resolution-1 sub-slots
   BlockStats* stats;
   uint32_t* live[2];
   VisEntry* vis;

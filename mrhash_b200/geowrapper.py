@@ -266,8 +266,8 @@ class GeoWrapper:
     def streamAllOut(self):
         check(self._lib.mrh_stream_all_out(self._h))
 
-    def extractMesh(self, filename):
-        check(self._lib.mrh_extract_mesh(self._h, None if filename is None else str(filename).encode()))
+    def extractMesh(self, filename, force_generic=False):
+        check(self._lib.mrh_extract_mesh_ex(self._h, None if filename is None else str(filename).encode(), int(force_generic)))
 
     def _mesh(self):
         v = C.POINTER(C.c_double)()

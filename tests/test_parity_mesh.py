@@ -1,0 +1,127 @@
+"""GPU parity of extractMesh (marching cubes) and serializeData against the unmodified reference
+kernels (oracle/_ref) on the same map state. Triangle order is atomic-append order in both
+implementations, so soups are compared as canonicalised sets."""
+import os
+
+import numpy as np
+import pytest
+
+from compare import canonical_triangles, compare_dumps
+from oracle_lib import Oracle, RefCuda, ref_available
+from test_parity_rgbd import NUM_BLOCKS, NUM_BUCKETS, feed, make_all
+
+from mrhash_b200 import GeoWrapper, synth
+
+pytestmark = pytest.mark.gpu
+
+MAX_TRIS = 2_000_000
+
+
+def build_state(n_frames, with_ref=True, width=640, height=480):
+    params = dict(synth.REPLICA_PARAMS)
+    fx, fy, cx, cy = synth.intrinsics(width, height)
+    ours = GeoWrapper(**params, num_sdf_blocks=NUM_BLOCKS, hash_num_buckets=NUM_BUCKETS, max_num_triangles=MAX_TRIS)
+    ours.setCamera(fx, fy, cx, cy, height, width, params["min_depth"], params["max_depth"], 0)
+    ref = None
+    if with_ref and ref_available():
+        ref = RefCuda(params, NUM_BLOCKS, NUM_BUCKETS, max_num_triangles=MAX_TRIS)
+        ref.set_camera(fx, fy, cx, cy, height, width, params["min_depth"], params["max_depth"], 0)
+    for k in range(n_frames):
+        # small steps so that voxels collect weight >= min_weight_threshold
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000, width=width, height=height)
+        feed(ours, [ref], t, q, depth, rgb)
+    return ours, ref, params
+
+
+def test_marching_cubes_matches_reference():
+    ours, ref, _ = build_state(8)
+    state = ours.dumpState()
+    if ref is not None:
+        assert compare_dumps(state, ref.dump())["ok"]
+    ours.extractMesh(None)
+    mine = ours.getTriangles()
+    assert len(mine) > 10000
+    # every block left the device (streamAllOut inside extractMesh) and sits in the host store
+    assert ours.getStats()["live_blocks"] == 0 and ours.storeSize() == len(state[0])
+    V, F, C = ours.getVertices(), ours.getFaces(), ours.getColors()
+    assert F.min() >= 0 and F.max() < len(V) and len(C) == len(V)
+    assert len(np.unique(V, axis=0)) == len(V)  # welded: no duplicate vertex
+    assert (F[:, 0] != F[:, 1]).all() and (F[:, 0] != F[:, 2]).all() and (F[:, 1] != F[:, 2]).all()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    theirs, n = ref.extract_triangles(MAX_TRIS)
+    assert n == len(theirs)
+    print(f"triangles ours={len(mine)} ref={n}")
+    assert len(mine) == n
+    a, b = canonical_triangles(mine, 6), canonical_triangles(theirs, 6)
+    diff = np.abs(a - b).max()
+    print("max |vertex diff| after canonical sort:", diff)
+    assert diff <= 1e-6
+    # bit-exact positions and colours as multisets
+    ka = np.sort(np.ascontiguousarray(mine.reshape(len(mine), -1)).view([("", mine.dtype)] * 18).ravel())
+    kb = np.sort(np.ascontiguousarray(theirs.reshape(len(theirs), -1)).view([("", theirs.dtype)] * 18).ravel())
+    same = int((ka == kb).sum())
+    print(f"bit-identical triangles: {same}/{n}")
+    assert same == n
+
+
+def test_halo_path_equals_generic_path():
+    """The shared-memory sampler and the per-read hash sampler must give the same soup bit for bit."""
+    a, _, _ = build_state(6, with_ref=False)
+    b, _, _ = build_state(6, with_ref=False)
+    a.extractMesh(None)
+    b.extractMesh(None, force_generic=True)
+    ta, tb = a.getTriangles(), b.getTriangles()
+    assert len(ta) == len(tb) and len(ta) > 0
+    ka = np.sort(np.ascontiguousarray(ta.reshape(len(ta), -1)).view([("", ta.dtype)] * 18).ravel())
+    kb = np.sort(np.ascontiguousarray(tb.reshape(len(tb), -1)).view([("", tb.dtype)] * 18).ravel())
+    assert (ka == kb).all()
+
+
+def _read_ply_points(path):
+    with open(path, "rb") as f:
+        header = b""
+        while not header.endswith(b"end_header\n"):
+            header += f.readline()
+        data = f.read()
+    lines = header.decode().split("\n")
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
+    props = [l.split()[1:] for l in lines if l.startswith("property")]
+    dt = np.dtype([(name, {"float": "<f4", "uchar": "u1"}[t]) for t, name in props])
+    return np.frombuffer(data, dt, n), [name for _, name in props]
+
+
+def test_serialize_data_round_trip(tmp_path):
+    """serializeData (streamer.cpp:104-160): one point per voxel with weight > 0, one per block."""
+    ours, _, params = build_state(3, with_ref=False)
+    entries, voxels = ours.dumpState()
+    ours.streamAllOut()
+    hp, vp = str(tmp_path / "hash.ply"), str(tmp_path / "voxel.ply")
+    ours.serializeData(hp, vp)
+    hpts, hprops = _read_ply_points(hp)
+    vpts, vprops = _read_ply_points(vp)
+    assert vprops == ["x", "y", "z", "sdf", "weight", "red", "green", "blue", "alpha"]
+    assert hprops == ["x", "y", "z", "weight", "red", "green", "blue", "alpha"]
+    w = voxels["weight"]
+    assert len(vpts) == int((w > 0).sum())
+    assert len(hpts) == int(((w > 0).sum(axis=1) > 0).sum())
+    assert (vpts["red"] == 255).all() and (vpts["green"] == 0).all()
+    # voxel positions / sdf / weight against the dump
+    s = np.float32(params["virtual_voxel_size"])
+    bi, vi = np.nonzero(w > 0)
+    lx, ly, lz = vi % 8, (vi // 8) % 8, vi // 64
+    exp = np.stack(
+        [
+            (entries[bi, 0] * 8).astype(np.float32) * s + lx.astype(np.float32) * s,
+            (entries[bi, 1] * 8).astype(np.float32) * s + ly.astype(np.float32) * s,
+            (entries[bi, 2] * 8).astype(np.float32) * s + lz.astype(np.float32) * s,
+            voxels["sdf"][bi, vi],
+            w[bi, vi].astype(np.float32),
+        ],
+        axis=1,
+    )
+    got = np.stack([vpts["x"], vpts["y"], vpts["z"], vpts["sdf"], vpts["weight"]], axis=1)
+    assert np.array_equal(exp[np.lexsort(exp.T[::-1])], got[np.lexsort(got.T[::-1])])
+    # a second streamAllOut + clearBuffers leaves nothing behind
+    ours.clearBuffers()
+    assert ours.storeSize() == 0
