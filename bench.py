@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
-COUNTERS_BYTES = 112  # sizeof(mrh::Counters)
+COUNTERS_BYTES = 120  # sizeof(mrh::Counters)
 
 
 def parse():

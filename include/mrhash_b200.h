@@ -69,6 +69,7 @@ typedef struct {
   uint64_t live_blocks;    /* currently allocated */
   int64_t heap_free;       /* getHeapHighFreeCount() (voxel_data_structures.cpp:148-153) */
   int64_t heap_low_free;
+  uint64_t dropped_updates; /* point-cloud path: update records beyond the staging capacity (0 in a healthy run) */
 } mrh_stats;
 
 /* record format of mrh_dump_state (test / parity only) */

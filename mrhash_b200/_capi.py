@@ -50,6 +50,7 @@ class Stats(C.Structure):
         ("live_blocks", C.c_uint64),
         ("heap_free", C.c_int64),
         ("heap_low_free", C.c_int64),
+        ("dropped_updates", C.c_uint64),
     ]
 
     def as_dict(self):

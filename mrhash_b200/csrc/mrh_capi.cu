@@ -119,6 +119,8 @@ static void free_map(mrh_map* m) {
       cudaEventDestroy(m->ev_points[i]);
   }
   cudaFree(m->d_tri), cudaFree(m->d_tri_count);
+  cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
+  cudaFreeHost(m->h_n_updates);
   cudaFreeHost(m->h_ctr);
   for (int i = 0; i < 8; ++i)
     if (m->ev_k[i])
@@ -235,6 +237,7 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
     CK(cudaEventCreateWithFlags(&m->ev_points[i], cudaEventDisableTiming));
   }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
+  CK(cudaMallocHost(&m->h_n_updates, sizeof(uint32_t)));
   for (int i = 0; i < 8; ++i)
     CK(cudaEventCreate(&m->ev_k[i]));
   cudaDeviceProp prop;
@@ -523,6 +526,7 @@ int mrh_get_stats(mrh_map* m, mrh_stats* out) {
   out->live_blocks    = (uint64_t) ((int64_t) m->num_sdf_blocks - ((int64_t) c.heap_counter + 1)) - c.low_parents + c.low_live;
   out->heap_free      = (int64_t) c.heap_counter + 1;
   out->heap_low_free  = (int64_t) c.heap_low_counter + 1;
+  out->dropped_updates = c.dropped_updates;
   return 0;
 }
 

@@ -124,6 +124,14 @@ struct mrh_map {
   double kernel_ms[8]{};
   uint64_t kernel_launches[8]{};
 
+  // point-cloud path staging: (voxel address, point index) keys + sdf values, double buffered for the sort
+  unsigned long long* d_upd_keys[2]{};
+  float* d_upd_vals[2]{};
+  size_t upd_cap       = 0;
+  void* d_sort_tmp     = nullptr;
+  size_t sort_tmp_bytes = 0;
+  uint32_t* h_n_updates = nullptr; // pinned
+
   // meshing
   float* d_tri           = nullptr;
   size_t d_tri_cap       = 0;

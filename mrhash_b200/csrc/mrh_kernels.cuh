@@ -15,6 +15,50 @@
 
 namespace mrh {
 
+// Warp-cooperative block walk shared by the RGB-D and point-cloud allocation kernels: every lane
+// advances its own DDA; per step the distinct unresolved keys of the warp are inserted once each.
+template <bool FRUSTUM_TEST>
+__device__ __forceinline__ void alloc_walk(const MapDev& m, const CameraDev& cam, const PoseDev& pose, uint32_t live_cur, DDA& dda, bool active, int lane) {
+  const unsigned full = 0xFFFFFFFFu;
+  const unsigned n_rays = __popc(__ballot_sync(full, active));
+  if (lane == 0 && n_rays)
+    atomicAdd(&m.ctr->rays_valid, (unsigned long long) n_rays);
+  int iter = 0;
+  // Keys this warp has already resolved (present, inserted or rejected by the frustum test): the
+  // outcome cannot change within the frame, and neighbouring rays revisit the same few blocks.
+  unsigned long long recent[4] = {kNoKey, kNoKey, kNoKey, kNoKey};
+  int recent_pos               = 0;
+  while (__any_sync(full, active)) {
+    unsigned long long key = kNoKey;
+    bool want              = false;
+    if (active) {
+      if (key_in_range(dda.cur)) {
+        key  = pack_key(dda.cur);
+        want = key != recent[0] && key != recent[1] && key != recent[2] && key != recent[3];
+      } else {
+        atomicAdd(&m.ctr->dropped_table, 1ull);
+      }
+    }
+    // one leader per distinct unresolved key in the warp
+    const unsigned peers = __match_any_sync(full, want ? key : kNoKey);
+    const bool leader    = want && (lane == __ffs(peers) - 1);
+    unsigned todo        = __ballot_sync(full, leader);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const i3 b = {__shfl_sync(full, dda.cur.x, src), __shfl_sync(full, dda.cur.y, src), __shfl_sync(full, dda.cur.z, src)};
+      warp_insert<FRUSTUM_TEST>(m, cam, pose, live_cur, b, lane);
+      recent[recent_pos] = pack_key(b);
+      recent_pos         = (recent_pos + 1) & 3;
+    }
+    if (active) {
+      active = dda.advance();
+      if (++iter >= kMaxDDA)
+        active = false;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_alloc_rgbd: one thread per pixel, one warp per 32-pixel row segment.
 // ---------------------------------------------------------------------------------------------
@@ -51,43 +95,7 @@ __global__ void __launch_bounds__(256) k_alloc_rgbd(MapDev m, FrameDev f, Camera
       }
     }
   }
-  const unsigned n_rays = __popc(__ballot_sync(full, active));
-  if (lane == 0 && n_rays)
-    atomicAdd(&m.ctr->rays_valid, (unsigned long long) n_rays);
-  int iter = 0;
-  // Keys this warp has already resolved (present, inserted or rejected by the frustum test): the
-  // outcome cannot change within the frame, and neighbouring rays revisit the same few blocks.
-  unsigned long long recent[4] = {kNoKey, kNoKey, kNoKey, kNoKey};
-  int recent_pos               = 0;
-  while (__any_sync(full, active)) {
-    unsigned long long key = kNoKey;
-    bool want              = false;
-    if (active) {
-      if (key_in_range(dda.cur)) {
-        key  = pack_key(dda.cur);
-        want = key != recent[0] && key != recent[1] && key != recent[2] && key != recent[3];
-      } else {
-        atomicAdd(&m.ctr->dropped_table, 1ull);
-      }
-    }
-    // one leader per distinct unresolved key in the warp
-    const unsigned peers = __match_any_sync(full, want ? key : kNoKey);
-    const bool leader    = want && (lane == __ffs(peers) - 1);
-    unsigned todo        = __ballot_sync(full, leader);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const i3 b = {__shfl_sync(full, dda.cur.x, src), __shfl_sync(full, dda.cur.y, src), __shfl_sync(full, dda.cur.z, src)};
-      warp_insert<true>(m, cam, pose, f.live_cur, b, lane);
-      recent[recent_pos] = pack_key(b);
-      recent_pos         = (recent_pos + 1) & 3;
-    }
-    if (active) {
-      active = dda.advance();
-      if (++iter >= kMaxDDA)
-        active = false;
-    }
-  }
+  alloc_walk<true>(m, cam, pose, f.live_cur, dda, active, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,204 @@
+// mrh_points.cuh — LiDAR / point-cloud integration kernels.
+//
+// Replaces allocBlocks3DKernel (voxel_data_structures.cu:925-1033) and integrate3DKernel
+// (:1215-1379). The reference updates voxels with a plain load / modify / store from one thread per
+// point, so several points racing on one voxel make its output run-to-run nondeterministic
+// (SURVEY.md H3). Here the walk and the update are split:
+//   k_points_emit  : one thread per point walks its voxel DDA and emits (voxel address, point
+//                    index, sdf) records - the set of records does not depend on voxel contents;
+//   (radix sort by (voxel address, point index))
+//   k_points_apply : one thread per distinct voxel folds its records in point order.
+// The result is deterministic and equals the reference's semantics with the points applied one
+// after another in index order (the CPU oracle's order).
+#pragma once
+#include "mrh_table.cuh"
+
+namespace mrh {
+
+constexpr int kPointIdxBits = 24; // up to 16.7 M points per cloud
+
+// ray end points of one point (shared by the allocation and integration walks)
+// for_alloc: allocBlocks3DKernel :939-961; else integrate3DKernel :1229-1250 (projective sdf)
+__device__ __forceinline__ bool point_ray(const MapDev& m, const PoseDev& pose, f3 pcam, bool for_alloc, float& range, float& trunc, f3& pw_min, f3& pw_max) {
+  range = norm3df(pcam.x, pcam.y, pcam.z);
+  if (for_alloc) {
+    if (range == 0.f)
+      return false;
+  } else if ((double) range < 1e-6 || range > m.max_integration_distance) {
+    return false;
+  }
+  const f3 dir     = normalize3(pcam);
+  trunc            = truncation(m.trunc, m.trunc_scale, range);
+  const float dmin = fminf(m.max_integration_distance, fsub(range, trunc));
+  const float dmax = fminf(m.max_integration_distance, fadd(range, trunc));
+  if (dmin >= dmax)
+    return false;
+  f3 a, b;
+  if (for_alloc) {
+    const float ka = fsub(dmin, range), kb = fsub(dmax, range);
+    a = {ffma(dir.x, ka, pcam.x), ffma(dir.y, ka, pcam.y), ffma(dir.z, ka, pcam.z)};
+    b = {ffma(dir.x, kb, pcam.x), ffma(dir.y, kb, pcam.y), ffma(dir.z, kb, pcam.z)};
+  } else {
+    a = {ffma(-dir.x, trunc, pcam.x), ffma(-dir.y, trunc, pcam.y), ffma(-dir.z, trunc, pcam.z)};
+    b = {ffma(dir.x, trunc, pcam.x), ffma(dir.y, trunc, pcam.y), ffma(dir.z, trunc, pcam.z)};
+  }
+  pw_min = se3_mul(pose.R, pose.t, a);
+  pw_max = se3_mul(pose.R, pose.t, b);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ points, uint32_t n_points) {
+  __shared__ PoseDev pose;
+  if (threadIdx.x == 0) {
+    load_pose(f, pose);
+    if (blockIdx.x == 0) {
+      m.ctr->live_count[f.live_cur ^ 1u] = 0;
+      m.ctr->vis_count                   = 0;
+      m.ctr->n_updates                   = 0;
+    }
+  }
+  __syncthreads();
+  const int lane   = threadIdx.x & 31;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active      = false;
+  DDA dda;
+  if (i < n_points) {
+    const f3 p = {__ldg(points + 3 * (size_t) i), __ldg(points + 3 * (size_t) i + 1), __ldg(points + 3 * (size_t) i + 2)};
+    float range, trunc;
+    f3 a, b;
+    if (point_ray(m, pose, p, true, range, trunc, a, b)) {
+      dda.init(a, b, m.voxel_size, m.ext, true);
+      active = true;
+    }
+  }
+  alloc_walk<false>(m, cam, pose, f.live_cur, dda, active, lane);
+}
+
+// One thread per point: voxel-level DDA, one record per visited voxel of an allocated block.
+__global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const float* __restrict__ points, uint32_t n_points, unsigned long long* __restrict__ keys, float* __restrict__ vals, uint32_t capacity) {
+  __shared__ PoseDev pose;
+  if (threadIdx.x == 0)
+    load_pose(f, pose);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points || m.ctr->vis_count == 0) // integrate3D runs only when current_occupied_blocks_ > 0 (:1387)
+    return;
+  const f3 p = {__ldg(points + 3 * (size_t) i), __ldg(points + 3 * (size_t) i + 1), __ldg(points + 3 * (size_t) i + 2)};
+  float range, trunc;
+  f3 a, b;
+  if (!point_ray(m, pose, p, false, range, trunc, a, b))
+    return;
+  DDA dda;
+  dda.init(a, b, m.voxel_size, m.ext, false);
+  // consecutive voxels of a ray mostly share a block: remember the last lookup
+  i3 last_b         = {INT_MIN, 0, 0};
+  uint32_t last_val = kInvalid;
+#pragma unroll 1
+  for (int iter = 0; iter < kMaxDDA; ++iter) {
+    const i3 v  = dda.cur;
+    const i3 bl = voxel_to_block(v, m.voxel_size, m.ext);
+    if (bl.x != last_b.x || bl.y != last_b.y || bl.z != last_b.z) {
+      const int slot = table_find(m, bl);
+      last_val       = slot >= 0 ? m.vals[slot] : kInvalid;
+      last_b         = bl;
+    }
+    if (last_val != kInvalid) {
+      const int r     = (int) (last_val >> 31);
+      const int scale = 1 << r;
+      const float vs  = fmul(m.voxel_size, i2f(scale));
+      const f3 vp     = {fmul(i2f(v.x / scale), vs), fmul(i2f(v.y / scale), vs), fmul(i2f(v.z / scale), vs)};
+      const f3 vc     = se3_mul(pose.Ri, pose.ti, vp);
+      float sdf       = fsub(range, norm3df(vc.x, vc.y, vc.z));
+      if (sdf <= -trunc)
+        break;
+      sdf = (sdf >= 0.f) ? fminf(trunc, sdf) : fmaxf(-trunc, sdf);
+      // reference pool address: entry.ptr + virtualVoxelPosToSDFBlockIndex(v, 8 / scale) (:1343)
+      int lx = v.x % 8, ly = v.y % 8, lz = v.z % 8;
+      lx += lx < 0 ? 8 : 0, ly += ly < 0 ? 8 : 0, lz += lz < 0 ? 8 : 0;
+      lx >>= r, ly >>= r, lz >>= r;
+      const unsigned long long addr = (r ? (unsigned long long) (last_val & 0x7FFFFFFFu) * 64ull : (unsigned long long) last_val * 512ull) + (unsigned long long) (lz * 64 + ly * 8 + lx);
+      const uint32_t o              = atomicAdd(&m.ctr->n_updates, 1u);
+      if (o < capacity) {
+        keys[o] = (addr << kPointIdxBits) | (unsigned long long) i;
+        vals[o] = sdf;
+      }
+    }
+    if (!dda.advance())
+      break;
+  }
+}
+
+// pointers to the three words of the voxel at a reference pool address (see read_voxel_addr)
+__device__ __forceinline__ bool voxel_words(const MapDev& m, unsigned long long addr, float*& sdf, float*& ss, uint32_t*& cw) {
+  const unsigned long long P = addr >> 9;
+  const uint32_t w           = (uint32_t) (addr & 511ull);
+  if (P >= m.num_blocks)
+    return false;
+  uint8_t* base = m.pool + (size_t) P * kBlockBytes;
+  if (m.carved[P]) {
+    base += (w >> 6) * 768u;
+    sdf = reinterpret_cast<float*>(base) + (w & 63u);
+    ss  = reinterpret_cast<float*>(base + 256) + (w & 63u);
+    cw  = reinterpret_cast<uint32_t*>(base + 512) + (w & 63u);
+  } else {
+    sdf = reinterpret_cast<float*>(base) + w;
+    ss  = reinterpret_cast<float*>(base + kPlaneBytes) + w;
+    cw  = reinterpret_cast<uint32_t*>(base + 2 * kPlaneBytes) + w;
+  }
+  return true;
+}
+
+// One thread per run of equal voxel address in the sorted record list.
+__global__ void __launch_bounds__(256) k_points_apply(MapDev m, const unsigned long long* __restrict__ keys, const float* __restrict__ vals, uint32_t capacity) {
+  const uint32_t n = min(m.ctr->n_updates, capacity);
+  const float half = fmul(m.voxel_size, 0.5f);
+  const float wn_f = __uint2float_rn((uint32_t) m.weight_sample);
+  unsigned long long updated = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long addr = keys[i] >> kPointIdxBits;
+    if (i > 0 && (keys[i - 1] >> kPointIdxBits) == addr)
+      continue; // not the head of its run
+    float *psdf, *pss;
+    uint32_t* pcw;
+    if (!voxel_words(m, addr, psdf, pss, pcw))
+      continue;
+    float sdf0  = *psdf;
+    float ss0   = *pss;
+    uint32_t cw = *pcw;
+    for (uint32_t j = i; j < n && (keys[j] >> kPointIdxBits) == addr; ++j) {
+      // integrate3DKernel :1333-1357 + combineVoxel (voxel_hash_utils.cuh:169-181), no colour input
+      const float sdf       = vals[j];
+      const uint32_t w0     = cw >> 24;
+      const float curr_mean = w0 > 0 ? sdf0 : 0.f;
+      const float delta     = fdiv(fsub(sdf, curr_mean), half);
+      const uint32_t wsum   = w0 + (uint32_t) m.weight_sample;
+      const float merged    = fdiv(ffma(sdf, wn_f, fmul(sdf0, __uint2float_rn(w0))), __uint2float_rn(wsum));
+      const uint32_t r0 = cw & 0xFF, g0 = (cw >> 8) & 0xFF, b0 = (cw >> 16) & 0xFF;
+      const uint32_t rr = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(r0), 0.5f)), 0.5f)) & 0xFF;
+      const uint32_t gg = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(g0), 0.5f)), 0.5f)) & 0xFF;
+      const uint32_t bb = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(b0), 0.5f)), 0.5f)) & 0xFF;
+      const uint32_t wn = min(wsum, (uint32_t) kWeightMax);
+      const float delta2 = fdiv(fsub(sdf, merged), half);
+      float ss           = fmul(delta, delta2);
+      if (fabsf(ss) < 1.175494350822287508e-38f)
+        ss = 0.f;
+      sdf0 = merged;
+      ss0  = fadd(0.f, ss);
+      cw   = rr | (gg << 8) | (bb << 16) | (wn << 24);
+      ++updated;
+    }
+    *psdf = sdf0, *pss = ss0, *pcw = cw;
+  }
+  // warp-aggregated statistics
+  for (int o = 16; o > 0; o >>= 1)
+    updated += __shfl_xor_sync(0xFFFFFFFFu, updated, o);
+  if ((threadIdx.x & 31) == 0 && updated)
+    atomicAdd(&m.ctr->voxels_updated, updated);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&m.ctr->blocks_visible, (unsigned long long) m.ctr->vis_count);
+    if (m.ctr->n_updates > capacity)
+      atomicAdd(&m.ctr->dropped_updates, (unsigned long long) (m.ctr->n_updates - capacity));
+  }
+}
+
+} // namespace mrh

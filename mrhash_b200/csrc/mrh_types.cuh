@@ -37,7 +37,7 @@ struct Counters {
   uint32_t vis_count;
   uint32_t n_realloc;
   uint32_t n_reintegrate;
-  uint32_t pad0;
+  uint32_t n_updates;    // point-cloud path: records emitted this frame
   // per-run totals (read back on demand)
   unsigned long long rays_valid;
   unsigned long long blocks_new;
@@ -47,6 +47,7 @@ struct Counters {
   unsigned long long blocks_realloc;
   unsigned long long dropped_heap;   // allocBlock "mem size exceed" events
   unsigned long long dropped_table;  // probe sequence exhausted / coordinate out of key range
+  unsigned long long dropped_updates; // point-cloud records beyond the staging capacity
   // map state (not reset by mrh_reset_stats)
   unsigned long long low_parents;    // pool blocks carved into 64-voxel sub-slots
   unsigned long long low_live;       // live resolution-1 blocks
