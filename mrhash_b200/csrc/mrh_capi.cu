@@ -86,6 +86,7 @@ static int alloc_map(mrh_map* m) {
   CK(cudaMalloc(&d.live[1], sizeof(uint32_t) * N * 2));
   CK(cudaMalloc(&d.vis, sizeof(VisEntry) * N * 2));
   CK(cudaMalloc(&d.realloc_list, sizeof(VisEntry) * N));
+  CK(cudaMalloc(&d.reint_keys, sizeof(unsigned long long) * N));
   CK(cudaMalloc(&d.ctr, sizeof(Counters)));
   return 0;
 }
@@ -107,7 +108,7 @@ int mrh::reset_map(mrh_map* m) {
 static void free_map(mrh_map* m) {
   MapDev& d = m->dev;
   cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.carved), cudaFree(d.stats);
-  cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.ctr), cudaFree(d.zbuf);
+  cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.reint_keys), cudaFree(d.ctr), cudaFree(d.zbuf);
   cudaFree(m->d_depth), cudaFree(m->d_rgb), cudaFree(m->d_points);
   for (int i = 0; i < 2; ++i) {
     cudaFreeHost(m->h_depth[i]), cudaFreeHost(m->h_rgb[i]), cudaFreeHost(m->h_points[i]);

@@ -1,8 +1,9 @@
 // mrh_frame.cu — per-frame launch sequence of the integration path.
 //
 // VoxelContainer::integrate (voxel_data_structures.cpp:90-134) issues ~12 kernels, ~10 blocking
-// copies and ~15 device synchronisations per frame. Here a frame is 3 kernels on one stream
-// (5 more on the every-n-th starve frame) and the host never waits.
+// copies and ~15 device synchronisations per frame. Here an RGB-D frame is 3 kernels on one stream
+// (4 more on the every-n-th starve frame) and the host never waits; the point-cloud path waits once
+// per frame for a 4-byte record count (the sort needs it).
 #include <algorithm>
 #include <cmath>
 
@@ -11,6 +12,7 @@
 #include "mrh_host.h"
 #include "mrh_kernels.cuh"
 #include "mrh_points.cuh"
+#include "mrh_var.cuh"
 
 namespace mrh {
 
@@ -34,49 +36,150 @@ FrameDev make_frame(const mrh_map* m) {
   return f;
 }
 
-static int gc_tail(mrh_map* m, const FrameDev& f, bool starve);
+namespace {
+
+  struct FrameCtx {
+    mrh_map* m;
+    FrameDev f;
+    bool gc, starve, var, var_active;
+    int grid_blocks, grid_list;
+  };
+
+  FrameCtx begin_frame(mrh_map* m) {
+    FrameCtx c;
+    c.m            = m;
+    c.f            = make_frame(m);
+    const int n_gc = m->p.n_frames_invalidate_voxels;
+    c.gc           = n_gc > 0;                                                                 // voxel_data_structures.cpp:105
+    c.starve       = c.gc && m->frame_index > 0 && (m->frame_index % (uint32_t) n_gc) == 0;    // :140
+    c.var          = m->p.sdf_var_threshold > 0.f;
+    c.var_active   = c.var && m->frame_index > 0;                                              // :99
+    c.grid_blocks  = m->num_sms * 8;
+    c.grid_list    = m->num_sms * 4;
+    return c;
+  }
+
+  // allocBlocks :885-891 / allocBlocks3D :1050-1056
+  int top_up_low_heap(FrameCtx& c) {
+    mrh_map* m = c.m;
+    const uint32_t low_blocks = (uint32_t) ((float) m->num_sdf_blocks * 0.1f); // voxel_data_structures.cuh:60
+    k_carve_decide<<<1, 1, 0, m->stream>>>(m->dev, low_blocks);
+    k_carve_low<<<c.grid_list, 256, 0, m->stream>>>(m->dev, 0u);
+    m->launches += 2;
+    CKL();
+    return 0;
+  }
+
+  // GC tail when the fused kernel cannot be used (voxel_data_structures.cpp:137-145:
+  // [starve], identify, free)
+  int gc_tail(FrameCtx& c, const FrameDev& f) {
+    mrh_map* m         = c.m;
+    const MapDev& d    = m->dev;
+    const CameraDev& k = m->cam;
+    cudaStream_t s     = m->stream;
+    if (c.starve) {
+      if (cudaMemsetAsync(d.zbuf, 0xFF, sizeof(unsigned long long) * k.rows * k.cols, s) != cudaSuccess)
+        return fail("memset zbuf failed");
+      k_starve<0><<<c.grid_blocks, 128, 0, s>>>(d, f, k);
+      k_starve<1><<<c.grid_blocks, 128, 0, s>>>(d, f, k);
+      m->launches += 2;
+    }
+    k_identify<<<c.grid_blocks, 128, 0, s>>>(d);
+    k_gc_free<<<c.grid_blocks, 128, 0, s>>>(d, f);
+    m->launches += 2;
+    if (c.var) {
+      k_gc_low<<<c.grid_list, 128, 0, s>>>(d, f);
+      m->launches += 1;
+    }
+    CKL();
+    return 0;
+  }
+
+  // checkVarSDF + reallocBlocks + flatAndReduceHashTable (voxel_data_structures.cpp:99-103);
+  // returns the frame descriptor the rest of the frame must use (the live lists have swapped)
+  int variance_pass(FrameCtx& c, int use_frustum, FrameDev& f2) {
+    mrh_map* m      = c.m;
+    const MapDev& d = m->dev;
+    cudaStream_t s  = m->stream;
+    const uint32_t cur = c.f.live_cur;
+    k_check_var<<<c.grid_blocks, 64, 0, s>>>(d, c.f);
+    k_realloc_prepare<<<1, 1, 0, s>>>(d, cur);
+    k_realloc<<<c.grid_list, 128, 0, s>>>(d, cur ^ 1u);
+    f2          = c.f;
+    f2.live_cur = cur ^ 1u;
+    k_visible<<<c.grid_list, 256, 0, s>>>(d, f2, m->cam, use_frustum);
+    m->launches += 4;
+    CKL();
+    return 0;
+  }
+
+  void end_frame(FrameCtx& c, bool lists_swapped_twice) {
+    mrh_map* m = c.m;
+    if (!lists_swapped_twice)
+      m->live_cur ^= 1u;
+    m->frame_index++;
+    m->frames_total++;
+  }
+
+} // namespace
+
+// used by stream-in: make room for n_low resolution-1 blocks
+int carve_low_blocks(mrh_map* m, uint32_t n_low) {
+  if (n_low == 0)
+    return 0;
+  k_carve_low<<<m->num_sms * 4, 256, 0, m->stream>>>(m->dev, (n_low + 7u) / 8u);
+  m->launches += 1;
+  CKL();
+  return 0;
+}
 
 int integrate_rgbd(mrh_map* m) {
+  FrameCtx c         = begin_frame(m);
   const MapDev& d    = m->dev;
-  const CameraDev& c = m->cam;
-  const FrameDev f   = make_frame(m);
+  const CameraDev& k = m->cam;
+  const FrameDev& f  = c.f;
   cudaStream_t s     = m->stream;
-  const int n_gc     = m->p.n_frames_invalidate_voxels;
-  const bool gc      = n_gc > 0; // voxel_data_structures.cpp:105
-  const bool starve  = gc && m->frame_index > 0 && (m->frame_index % (uint32_t) n_gc) == 0; // :140
-  const bool var     = m->p.sdf_var_threshold > 0.f;
-
-  if (var)
-    return fail("sdf_var_threshold > 0 is not wired up yet");
-
-  const bool prof = m->profiling;
+  const bool prof    = m->profiling;
   auto mark = [&](int i) {
     if (prof)
       cudaEventRecord(m->ev_k[i], s);
   };
-  const dim3 grid_alloc((c.cols + 31) / 32, (c.rows + 7) / 8);
+  if (c.var && top_up_low_heap(c))
+    return 1;
+  const dim3 grid_alloc((k.cols + 31) / 32, (k.rows + 7) / 8);
   mark(0);
-  k_alloc_rgbd<<<grid_alloc, 256, 0, s>>>(d, f, c, m->depth_ptr);
+  k_alloc_rgbd<<<grid_alloc, 256, 0, s>>>(d, f, k, m->depth_ptr);
   CKL();
   mark(1);
-  k_visible<<<m->num_sms * 4, 256, 0, s>>>(d, f, c, 1);
+  k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 1);
   CKL();
   mark(2);
   m->launches += 2;
-  const int grid_blocks = m->num_sms * 8;
-  if (gc && !starve) {
-    k_integrate<true><<<grid_blocks, 128, 0, s>>>(d, f, c, m->depth_ptr, m->rgb_ptr);
-    CKL();
-    mark(3);
+  const bool fused_gc = c.gc && !c.starve && !c.var;
+  if (fused_gc)
+    k_integrate<true><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
+  else
+    k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
+  CKL();
+  mark(3);
+  m->launches += 1;
+  bool swapped_twice = false;
+  FrameDev f2        = f;
+  if (c.var) {
+    k_integrate_low<<<c.grid_list, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
     m->launches += 1;
-  } else {
-    k_integrate<false><<<grid_blocks, 128, 0, s>>>(d, f, c, m->depth_ptr, m->rgb_ptr);
     CKL();
-    mark(3);
-    m->launches += 1;
-    if (starve && gc_tail(m, f, true))
-      return 1;
+    if (c.var_active) {
+      if (variance_pass(c, 1, f2))
+        return 1;
+      k_reintegrate<<<c.grid_list, 128, 0, s>>>(d, f2, k, m->depth_ptr, m->rgb_ptr);
+      m->launches += 1;
+      CKL();
+      swapped_twice = true;
+    }
   }
+  if (c.gc && !fused_gc && gc_tail(c, f2))
+    return 1;
   if (prof) {
     // profiling pass only: wait for the frame and accumulate the per-kernel device times
     if (cudaEventSynchronize(m->ev_k[3]) != cudaSuccess)
@@ -88,80 +191,26 @@ int integrate_rgbd(mrh_map* m) {
       m->kernel_launches[i] += 1;
     }
   }
-  m->live_cur ^= 1u;
-  m->frame_index++;
-  m->frames_total++;
+  end_frame(c, swapped_twice);
   return 0;
 }
 
-// GC tail shared by both sensor paths when the fused kernel cannot be used
-// (voxel_data_structures.cpp:137-145: [starve], identify, free)
-static int gc_tail(mrh_map* m, const FrameDev& f, bool starve) {
-  const MapDev& d    = m->dev;
-  const CameraDev& c = m->cam;
-  cudaStream_t s     = m->stream;
-  const int grid     = m->num_sms * 8;
-  if (starve) {
-    if (cudaMemsetAsync(d.zbuf, 0xFF, sizeof(unsigned long long) * c.rows * c.cols, s) != cudaSuccess)
-      return fail("memset zbuf failed");
-    k_starve<0><<<grid, 128, 0, s>>>(d, f, c);
-    k_starve<1><<<grid, 128, 0, s>>>(d, f, c);
-    m->launches += 2;
-  }
-  k_identify<<<grid, 128, 0, s>>>(d);
-  k_gc_free<<<grid, 128, 0, s>>>(d, f);
-  m->launches += 2;
-  CKL();
-  return 0;
-}
-
-int integrate_points(mrh_map* m) {
-  const MapDev& d    = m->dev;
-  const CameraDev& c = m->cam;
-  const FrameDev f   = make_frame(m);
-  cudaStream_t s     = m->stream;
-  const int n_gc     = m->p.n_frames_invalidate_voxels;
-  const bool gc      = n_gc > 0;
-  const bool starve  = gc && m->frame_index > 0 && (m->frame_index % (uint32_t) n_gc) == 0;
-  const bool var     = m->p.sdf_var_threshold > 0.f;
-  const uint32_t n   = (uint32_t) m->n_points;
-  if (var)
-    return fail("sdf_var_threshold > 0 is not wired up yet");
-  if (m->n_points >= (1ull << kPointIdxBits))
-    return fail("point cloud too large: %zu points (limit %u)", m->n_points, 1u << kPointIdxBits);
-
-  // staging for the (voxel, point, sdf) records: a ray of length 2t crosses at most 3*(2t/size)+4 voxels
-  const float t_max   = m->p.sdf_truncation + m->p.sdf_truncation_scale * m->max_integration_distance;
-  const size_t per_pt = (size_t) std::min(3.0 * std::ceil(2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
-  const size_t want   = std::min<size_t>((size_t) n * per_pt, (size_t) 1 << 28);
-  if (want > m->upd_cap) {
-    cudaStreamSynchronize(s);
-    for (int i = 0; i < 2; ++i) {
-      cudaFree(m->d_upd_keys[i]), cudaFree(m->d_upd_vals[i]);
-      if (cudaMalloc(&m->d_upd_keys[i], sizeof(unsigned long long) * want) != cudaSuccess || cudaMalloc(&m->d_upd_vals[i], sizeof(float) * want) != cudaSuccess)
-        return fail("out of device memory for %zu point-update records", want);
-    }
-    m->upd_cap = want;
-    size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_upd_keys[0], m->d_upd_keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) want, 0, 64, s);
-    cudaFree(m->d_sort_tmp);
-    if (cudaMalloc(&m->d_sort_tmp, tmp) != cudaSuccess)
-      return fail("out of device memory for the sort workspace");
-    m->sort_tmp_bytes = tmp;
-  }
-
+// integrate3D (:1381-1401): emit -> sort -> apply
+static int fuse_points(FrameCtx& c, const FrameDev& f) {
+  mrh_map* m      = c.m;
+  const MapDev& d = m->dev;
+  cudaStream_t s  = m->stream;
+  const uint32_t n = (uint32_t) m->n_points;
   const int grid_pts = (int) ((n + 255) / 256);
-  k_alloc_points<<<grid_pts, 256, 0, s>>>(d, f, c, m->d_points, n);
-  CKL();
-  k_visible<<<m->num_sms * 4, 256, 0, s>>>(d, f, c, 0);
-  CKL();
+  if (cudaMemsetAsync(&d.ctr->n_updates, 0, sizeof(uint32_t), s) != cudaSuccess)
+    return fail("point path: clearing the record count failed");
   k_points_emit<<<grid_pts, 256, 0, s>>>(d, f, m->d_points, n, m->d_upd_keys[0], m->d_upd_vals[0], (uint32_t) m->upd_cap);
   CKL();
-  m->launches += 3;
-  // the sort needs the record count on the host: one 4-byte read-back per frame
+  m->launches += 1;
+  // the sort needs the record count on the host: one 4-byte read-back per pass
   if (cudaMemcpyAsync(m->h_n_updates, &d.ctr->n_updates, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
     return fail("point path: reading the record count failed: %s", cudaGetErrorString(cudaGetLastError()));
-  const uint32_t n_upd = (uint32_t) std::min<size_t>(*m->h_n_updates, m->upd_cap);
+  const uint32_t n_upd           = (uint32_t) std::min<size_t>(*m->h_n_updates, m->upd_cap);
   const unsigned long long* keys = m->d_upd_keys[0];
   const float* vals              = m->d_upd_vals[0];
   if (n_upd > 1) {
@@ -174,14 +223,67 @@ int integrate_points(mrh_map* m) {
     keys = m->d_upd_keys[1], vals = m->d_upd_vals[1];
     m->launches += 4;
   }
-  k_points_apply<<<m->num_sms * 4, 256, 0, s>>>(d, keys, vals, (uint32_t) m->upd_cap);
+  k_points_apply<<<c.grid_list, 256, 0, s>>>(d, keys, vals, (uint32_t) m->upd_cap);
   CKL();
   m->launches += 1;
-  if (gc && gc_tail(m, f, starve))
+  return 0;
+}
+
+int integrate_points(mrh_map* m) {
+  FrameCtx c         = begin_frame(m);
+  const MapDev& d    = m->dev;
+  const CameraDev& k = m->cam;
+  const FrameDev& f  = c.f;
+  cudaStream_t s     = m->stream;
+  const uint32_t n   = (uint32_t) m->n_points;
+  if (m->n_points >= (1ull << kPointIdxBits))
+    return fail("point cloud too large: %zu points (limit %u)", m->n_points, 1u << kPointIdxBits);
+
+  // staging for the (voxel, point, sdf) records: a ray of length 2t crosses at most 3*(2t/size)+4 voxels
+  const float t_max   = m->p.sdf_truncation + m->p.sdf_truncation_scale * m->max_integration_distance;
+  const size_t per_pt = (size_t) std::min(3.0 * std::ceil(2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
+  const size_t want   = std::min<size_t>((size_t) n * per_pt, (size_t) 1 << 28);
+  if (want > m->upd_cap) {
+    cudaStreamSynchronize(s);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(m->d_upd_keys[i]), cudaFree(m->d_upd_vals[i]);
+      m->d_upd_keys[i] = nullptr, m->d_upd_vals[i] = nullptr;
+      if (cudaMalloc(&m->d_upd_keys[i], sizeof(unsigned long long) * want) != cudaSuccess || cudaMalloc(&m->d_upd_vals[i], sizeof(float) * want) != cudaSuccess)
+        return fail("out of device memory for %zu point-update records", want);
+    }
+    m->upd_cap = want;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_upd_keys[0], m->d_upd_keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) want, 0, 64, s);
+    cudaFree(m->d_sort_tmp);
+    m->d_sort_tmp = nullptr;
+    if (cudaMalloc(&m->d_sort_tmp, tmp) != cudaSuccess)
+      return fail("out of device memory for the sort workspace");
+    m->sort_tmp_bytes = tmp;
+  }
+
+  if (c.var && top_up_low_heap(c))
     return 1;
-  m->live_cur ^= 1u;
-  m->frame_index++;
-  m->frames_total++;
+  const int grid_pts = (int) ((n + 255) / 256);
+  k_alloc_points<<<grid_pts, 256, 0, s>>>(d, f, k, m->d_points, n);
+  CKL();
+  k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 0);
+  CKL();
+  m->launches += 2;
+  if (fuse_points(c, f))
+    return 1;
+  bool swapped_twice = false;
+  FrameDev f2        = f;
+  if (c.var_active) {
+    if (variance_pass(c, 0, f2))
+      return 1;
+    // reintegrate3D re-launches the full integrate3DKernel (:1568): the frame is fused a second time (Q7)
+    if (fuse_points(c, f2))
+      return 1;
+    swapped_twice = true;
+  }
+  if (c.gc && gc_tail(c, f2))
+    return 1;
+  end_frame(c, swapped_twice);
   return 0;
 }
 

@@ -144,6 +144,7 @@ namespace mrh {
   int reset_map(mrh_map* m);
   int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels);
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
+  int carve_low_blocks(mrh_map* m, uint32_t n_low);
   int integrate_rgbd(mrh_map* m);
   int integrate_points(mrh_map* m);
   FrameDev make_frame(const mrh_map* m);

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(256) k_alloc_rgbd(MapDev m, FrameDev f, Camera
     if (blockIdx.x == 0 && blockIdx.y == 0) {
       // lists consumed by later kernels of this frame start empty
       m.ctr->live_count[f.live_cur ^ 1u] = 0;
-      m.ctr->vis_count                         = 0;
+      m.ctr->vis_count                   = 0;
+      m.ctr->n_realloc                   = 0;
     }
   }
   __syncthreads();

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, Came
       m.ctr->live_count[f.live_cur ^ 1u] = 0;
       m.ctr->vis_count                   = 0;
       m.ctr->n_updates                   = 0;
+      m.ctr->n_realloc                   = 0;
     }
   }
   __syncthreads();

@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
     if (n == 0)
       return 0;
+    uint32_t n_low = 0;
+    for (size_t i = 0; i < n; ++i)
+      n_low += recs[i].resolution != 0;
+    if (carve_low_blocks(m, n_low))
+      return 1;
     const size_t chunk   = std::min<size_t>(n, 1u << 16);
     GatherRecord* d_recs = nullptr;
     uint32_t* d_vox      = nullptr;

@@ -38,6 +38,8 @@ struct Counters {
   uint32_t n_realloc;
   uint32_t n_reintegrate;
   uint32_t n_updates;    // point-cloud path: records emitted this frame
+  uint32_t carve_request; // variance path: pool blocks to split into sub-slots this frame
+  uint32_t pad1;
   // per-run totals (read back on demand)
   unsigned long long rays_valid;
   unsigned long long blocks_new;
@@ -100,6 +102,7 @@ struct MapDev {
   uint32_t* live[2];
   VisEntry* vis;
   VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
+  unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate
   unsigned long long* zbuf;
   Counters* ctr;
 };
