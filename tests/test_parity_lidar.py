@@ -41,20 +41,25 @@ def test_lidar_stream(n_gc):
         ours.setPointCloud(pts, False)
         ours.compute()
         orc.compute_points(T, pts)
-        if ref is not None:
+        if ref is not None and k == 0 and n_gc == 0:
+            # The reference's voxel update is a racy read-modify-write: voxels hit by several points
+            # of one frame lose updates. Voxels touched by exactly ONE point cannot race, so after the
+            # first frame those must be bit-identical; the block set is race-free as well.
             ref.compute_points(T, pts)
+            (ea, va), (eb, vb) = ours.dumpState(), ref.dump()
+            assert np.array_equal(ea[:, :4], eb[:, :4])
+            once = va["weight"] == 1
+            assert once.sum() > 50000
+            assert (vb["weight"][once] == 1).all()
+            assert np.array_equal(va["sdf"][once].view(np.uint32), vb["sdf"][once].view(np.uint32))
+            lost = int((vb["weight"] < va["weight"]).sum())
+            print(f"[lidar frame 0 vs racy reference] single-hit voxels identical: {int(once.sum())}; voxels where the reference lost updates: {lost}")
     mine = ours.dumpState()
     st = ours.getStats()
     assert st["dropped_heap"] == 0 and st["dropped_table"] == 0 and st["dropped_updates"] == 0
     assert len(mine[0]) > 1000
     rep = compare_dumps(mine, orc.dump())
     print(f"[lidar gc={n_gc} ours-vs-oracle] " + ", ".join(f"{k}={v}" for k, v in rep.items()))
-    if ref is not None:
-        rr = compare_dumps(mine, ref.dump())
-        print(f"[lidar gc={n_gc} ours-vs-refcuda (racy)] " + ", ".join(f"{k}={v}" for k, v in rr.items()))
-        # identical block sets; the racy reference loses some concurrent updates
-        assert rr["only_a"] == 0 and rr["only_b"] == 0
-        assert rr["weight_mismatch"] <= 0.05 * (mine[1]["weight"] > 0).sum()
     # The oracle restates libdevice's norm3df exactly; only MUFU.RSQ (normalize) is not reproducible
     # on the CPU, so a DDA tie may resolve differently for a handful of rays: allow 1e-5 of the
     # voxels to differ (observed: 0), everything else must agree bit for bit.
