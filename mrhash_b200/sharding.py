@@ -1,0 +1,85 @@
+"""Multi-GPU partition of one map by hash-bucket range.
+
+GPU g of G owns the block keys whose reference hash bucket (calculateHash,
+/root/reference/mrhash/src/sdf/voxel_data_structures.cu:151-160) falls in
+[g*nb/G, (g+1)*nb/G). Every rank sees the whole frame (rank 0 ingests it and broadcasts it), walks
+all rays, but inserts / fuses / collects only the blocks it owns, so integration needs no exchange:
+a voxel update depends only on the frame and the voxel's own state. Meshing reads the 26 neighbour
+blocks, which under hash partitioning live on other ranks: blocks are exchanged once before it
+(`gather_blocks`).
+
+torch.distributed is plumbing only (NCCL on the GPU box, gloo in the CPU tests).
+"""
+import numpy as np
+
+P0, P1, P2 = 73856093, 19349669, 83492791  # params.h:102-104
+
+
+def block_hash(blocks, num_buckets):
+    """calculateHash for an int array [..., 3] of block coordinates."""
+    b = np.asarray(blocks).astype(np.int64)
+    u = b.astype(np.uint32).astype(np.uint64)
+    h = ((u[..., 0] * P0) & 0xFFFFFFFF) ^ ((u[..., 1] * P1) & 0xFFFFFFFF) ^ ((u[..., 2] * P2) & 0xFFFFFFFF)
+    return (h % np.uint64(num_buckets)).astype(np.int64)
+
+
+def bucket_range(rank, world, num_buckets):
+    """[lo, hi) of hash buckets owned by `rank` (same arithmetic as refresh_map_params in mrh_capi.cu)."""
+    if world <= 1:
+        return 0, int(num_buckets)
+    return int(num_buckets) * rank // world, int(num_buckets) * (rank + 1) // world
+
+
+def owner_of(blocks, world, num_buckets):
+    """Rank that owns each block of an int array [..., 3]."""
+    h = block_hash(blocks, num_buckets)
+    if world <= 1:
+        return np.zeros(h.shape, np.int64)
+    bounds = np.array([bucket_range(r, world, num_buckets)[1] for r in range(world)], np.int64)
+    return np.searchsorted(bounds, h, side="right")
+
+
+def broadcast_frame(depth, rgb, pose, src=0, group=None):
+    """Broadcast one frame (torch tensors, in place) from `src` to every rank.
+    depth f32 [H,W], rgb u8 [H,W,3], pose f32 [7] = translation + quaternion xyzw."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.broadcast(pose, src, group=group)
+    dist.broadcast(depth, src, group=group)
+    dist.broadcast(rgb, src, group=group)
+
+
+def gather_blocks(entries, voxels, dst=0, group=None, device="cpu"):
+    """Gather every rank's (entries [n,5] int32, voxels [n,512] VOXEL_DTYPE) on `dst`.
+    Returns the merged, key-sorted (entries, voxels) on dst and (None, None) elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return entries, voxels
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = torch.tensor([len(entries)], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    n_max = max(counts + [1])
+    e = torch.zeros((n_max, 5), dtype=torch.int32, device=device)
+    v = torch.zeros((n_max, 512 * 12), dtype=torch.uint8, device=device)
+    if len(entries):
+        e[: len(entries)] = torch.from_numpy(np.ascontiguousarray(entries)).to(device)
+        v[: len(entries)] = torch.from_numpy(np.ascontiguousarray(voxels).view(np.uint8).reshape(len(entries), -1)).to(device)
+    if rank == dst:
+        es = [torch.zeros_like(e) for _ in range(world)]
+        vs = [torch.zeros_like(v) for _ in range(world)]
+    else:
+        es = vs = None
+    dist.gather(e, es, dst=dst, group=group)
+    dist.gather(v, vs, dst=dst, group=group)
+    if rank != dst:
+        return None, None
+    ee = np.concatenate([es[r][: counts[r]].cpu().numpy() for r in range(world)])
+    vv = np.concatenate([vs[r][: counts[r]].cpu().numpy() for r in range(world)]).view(voxels.dtype).reshape(-1, 512)
+    order = np.lexsort((ee[:, 2], ee[:, 1], ee[:, 0]))
+    return ee[order], vv[order]

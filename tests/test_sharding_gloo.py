@@ -1,0 +1,91 @@
+"""CPU, world_size 2 (gloo): host-side logic of the multi-GPU partition (mrhash_b200/sharding.py)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mrhash_b200 import VOXEL_DTYPE, sharding, synth
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. frame broadcast: rank 0 ingests, everybody ends up with the same bytes
+        if rank == 0:
+            t, q, depth, rgb = synth.rgbd_frame(3, n_frames=100, width=64, height=48)
+            d, c, p = torch.from_numpy(depth), torch.from_numpy(rgb), torch.from_numpy(np.concatenate([t, q]).astype(np.float32))
+        else:
+            d, c, p = torch.zeros((48, 64)), torch.zeros((48, 64, 3), dtype=torch.uint8), torch.zeros(7)
+        sharding.broadcast_frame(d, c, p, src=0)
+        t, q, depth, rgb = synth.rgbd_frame(3, n_frames=100, width=64, height=48)
+        assert np.array_equal(d.numpy(), depth) and np.array_equal(c.numpy(), rgb)
+        assert np.array_equal(p.numpy(), np.concatenate([t, q]).astype(np.float32))
+        # 2. each rank "owns" the blocks of its bucket range; gathering them on rank 0 restores the set
+        rng = np.random.default_rng(0)
+        blocks = np.unique(rng.integers(-40, 40, size=(500, 3)), axis=0).astype(np.int32)
+        nb = 1000
+        mine = blocks[sharding.owner_of(blocks, world, nb) == rank]
+        lo, hi = sharding.bucket_range(rank, world, nb)
+        h = sharding.block_hash(mine, nb)
+        assert ((h >= lo) & (h < hi)).all()
+        entries = np.concatenate([mine, np.zeros((len(mine), 2), np.int32)], axis=1)
+        voxels = np.zeros((len(mine), 512), VOXEL_DTYPE)
+        voxels["sdf"] = mine[:, :1].astype(np.float32)
+        voxels["weight"] = rank + 1
+        ee, vv = sharding.gather_blocks(entries, voxels, dst=0)
+        if rank == 0:
+            order = np.lexsort((blocks[:, 2], blocks[:, 1], blocks[:, 0]))
+            assert np.array_equal(ee[:, :3], blocks[order])
+            assert np.array_equal(vv["sdf"][:, 0], blocks[order][:, 0].astype(np.float32))
+            owners = sharding.owner_of(ee[:, :3], world, nb)
+            assert np.array_equal(vv["weight"][:, 0], owners + 1)
+        else:
+            assert ee is None and vv is None
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover
+        out.put((rank, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_and_exchange_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: "ok", 1: "ok"}, results
+
+
+def test_bucket_ranges_partition_the_table():
+    for world in (1, 2, 3, 4, 8):
+        for nb in (7, 1000, 250000):
+            edges = [sharding.bucket_range(r, world, nb) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == nb
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+
+
+def test_block_hash_known_answers():
+    # values derived from the formula of calculateHash
+    assert sharding.block_hash([0, 0, 0], 250000) == 0
+    assert sharding.block_hash([1, 2, 3], 250000) == 163698
+    assert sharding.block_hash([1, 2, 3], 500000) == 163698
+    assert sharding.block_hash([-1, -1, -1], 250000) == 112177
+    assert sharding.block_hash([25, -12, 7], 250000) == 205824
+    assert sharding.block_hash([25, -12, 7], 500000) == 455824
+    assert sharding.block_hash([1000, -1000, 12345], 250000) == 184207
