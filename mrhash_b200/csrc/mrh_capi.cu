@@ -82,8 +82,8 @@ static int alloc_map(mrh_map* m) {
   CK(cudaMalloc(&d.pool, (size_t) kBlockBytes * N));
   CK(cudaMalloc(&d.carved, N));
   CK(cudaMalloc(&d.stats, sizeof(BlockStats) * N));
-  CK(cudaMalloc(&d.live[0], sizeof(uint32_t) * N * 2));
-  CK(cudaMalloc(&d.live[1], sizeof(uint32_t) * N * 2));
+  CK(cudaMalloc(&d.live[0], sizeof(LiveEntry) * N * 2));
+  CK(cudaMalloc(&d.live[1], sizeof(LiveEntry) * N * 2));
   CK(cudaMalloc(&d.vis, sizeof(VisEntry) * N * 2));
   CK(cudaMalloc(&d.realloc_list, sizeof(VisEntry) * N));
   CK(cudaMalloc(&d.reint_keys, sizeof(unsigned long long) * N));
@@ -100,7 +100,8 @@ int mrh::reset_map(mrh_map* m) {
   k_init_heap<<<592, 256, 0, m->stream>>>(d.heap, d.stats, d.num_blocks);
   k_init_counters<<<1, 1, 0, m->stream>>>(d.ctr, d.num_blocks);
   m->launches += 2;
-  m->live_cur = 0;
+  m->live_cur       = 0;
+  m->counters_clean = true;
   CK(cudaGetLastError());
   return 0;
 }
@@ -109,16 +110,16 @@ static void free_map(mrh_map* m) {
   MapDev& d = m->dev;
   cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.carved), cudaFree(d.stats);
   cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.reint_keys), cudaFree(d.ctr), cudaFree(d.zbuf);
-  cudaFree(m->d_depth), cudaFree(m->d_rgb), cudaFree(m->d_points);
-  for (int i = 0; i < 2; ++i) {
-    cudaFreeHost(m->h_depth[i]), cudaFreeHost(m->h_rgb[i]), cudaFreeHost(m->h_points[i]);
-    if (m->ev_depth[i])
-      cudaEventDestroy(m->ev_depth[i]);
-    if (m->ev_rgb[i])
-      cudaEventDestroy(m->ev_rgb[i]);
-    if (m->ev_points[i])
-      cudaEventDestroy(m->ev_points[i]);
-  }
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(in->d_buf[i]), cudaFreeHost(in->h_buf[i]);
+      if (in->copied[i])
+        cudaEventDestroy(in->copied[i]);
+      if (in->consumed[i])
+        cudaEventDestroy(in->consumed[i]);
+    }
+  if (m->copy_stream)
+    cudaStreamDestroy(m->copy_stream);
   cudaFree(m->d_tri), cudaFree(m->d_tri_count);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_n_updates);
@@ -158,30 +159,49 @@ static void refresh_map_params(mrh_map* m) {
   }
 }
 
-// Ingest: copy into one of two pinned staging buffers and queue the H2D copy immediately, so the
-// transfer of frame k+1 overlaps the kernels of frame k (the reference does a blocking
-// DualMatrix::toDevice inside compute(), cuda_matrix.cuh:129).
+// Ingest (replaces the blocking DualMatrix::toDevice inside compute(), cuda_matrix.cuh:129).
+// The copy goes to the other device image on the copy stream, after the frame that last read that
+// image has finished. Pinned caller memory is copied from directly and the call waits for the
+// transfer (setters copy: the caller may reuse its buffer on return); pageable memory goes through
+// a pinned staging buffer and the call returns once the bytes are staged.
 template <typename T, typename F>
-static int stage_upload(mrh_map* m, T** h_buf, size_t* h_cap, cudaEvent_t* ev, int* which, T** d_buf, size_t* d_cap, size_t n, F fill) {
-  if (n > *d_cap) {
-    CK(cudaStreamSynchronize(m->stream));
-    cudaFree(*d_buf);
-    *d_buf = nullptr;
-    CK(cudaMalloc(d_buf, sizeof(T) * n));
-    *d_cap = n;
+static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n, F fill) {
+  const int w        = in.which ^ 1;
+  const size_t bytes = sizeof(T) * n;
+  if (bytes > in.d_cap[w]) {
+    CK(cudaEventSynchronize(in.consumed[w]));
+    cudaFree(in.d_buf[w]);
+    in.d_buf[w] = nullptr;
+    CK(cudaMalloc(&in.d_buf[w], bytes));
+    in.d_cap[w] = bytes;
   }
-  const int w = *which ^= 1;
-  if (n > h_cap[w]) {
-    CK(cudaEventSynchronize(ev[w]));
-    cudaFreeHost(h_buf[w]);
-    h_buf[w] = nullptr;
-    CK(cudaMallocHost(&h_buf[w], sizeof(T) * n));
-    h_cap[w] = n;
+  CK(cudaStreamWaitEvent(m->copy_stream, in.consumed[w], 0));
+  bool direct = false;
+  if (src_or_null) {
+    cudaPointerAttributes attr;
+    direct = cudaPointerGetAttributes(&attr, src_or_null) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
   }
-  CK(cudaEventSynchronize(ev[w])); // the copy that last read this staging buffer has finished
-  fill(h_buf[w]);
-  CK(cudaMemcpyAsync(*d_buf, h_buf[w], sizeof(T) * n, cudaMemcpyHostToDevice, m->stream));
-  CK(cudaEventRecord(ev[w], m->stream));
+  if (direct) {
+    CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    CK(cudaEventRecord(in.copied[w], m->copy_stream));
+    CK(cudaEventSynchronize(in.copied[w]));
+  } else {
+    if (bytes > in.h_cap[w]) {
+      CK(cudaEventSynchronize(in.copied[w]));
+      cudaFreeHost(in.h_buf[w]);
+      in.h_buf[w] = nullptr;
+      CK(cudaMallocHost(&in.h_buf[w], bytes));
+      in.h_cap[w] = bytes;
+    }
+    CK(cudaEventSynchronize(in.copied[w])); // the transfer that last read this staging buffer has finished
+    fill((T*) in.h_buf[w]);
+    CK(cudaMemcpyAsync(in.d_buf[w], in.h_buf[w], bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    CK(cudaEventRecord(in.copied[w], m->copy_stream));
+  }
+  in.which  = w;
+  in.active = true;
+  m->h2d_bytes += bytes;
   return 0;
 }
 
@@ -232,11 +252,12 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&m->ev0));
   CK(cudaEventCreate(&m->ev1));
-  for (int i = 0; i < 2; ++i) {
-    CK(cudaEventCreateWithFlags(&m->ev_depth[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_rgb[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&m->ev_points[i], cudaEventDisableTiming));
-  }
+  CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&in->copied[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&in->consumed[i], cudaEventDisableTiming));
+    }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
   CK(cudaMallocHost(&m->h_n_updates, sizeof(uint32_t)));
   for (int i = 0; i < 8; ++i)
@@ -356,10 +377,9 @@ int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols) {
   if (!depth || rows <= 0 || cols <= 0)
     return fail("GeoWrapper::setDepthImage|input should be a 2D numpy array");
   const size_t n = (size_t) rows * cols;
-  if (stage_upload(m, m->h_depth, m->h_depth_cap, m->ev_depth, &m->depth_which, &m->d_depth, &m->d_depth_cap, n, [&](float* dst) { memcpy(dst, depth, sizeof(float) * n); }))
+  if (ingest_upload<float>(m, m->in_depth, depth, n, [&](float* dst) { memcpy(dst, depth, sizeof(float) * n); }))
     return 1;
-  m->depth_ptr = m->d_depth, m->depth_rows = rows, m->depth_cols = cols;
-  m->h2d_bytes += sizeof(float) * n;
+  m->depth_ptr = (const float*) m->in_depth.d_buf[m->in_depth.which], m->depth_rows = rows, m->depth_cols = cols;
   return 0;
 }
 
@@ -368,10 +388,9 @@ int mrh_set_rgb(mrh_map* m, const uint8_t* rgb, int rows, int cols) {
   if (!rgb || rows <= 0 || cols <= 0)
     return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
   const size_t n = (size_t) rows * cols * 3;
-  if (stage_upload(m, m->h_rgb, m->h_rgb_cap, m->ev_rgb, &m->rgb_which, &m->d_rgb, &m->d_rgb_cap, n, [&](uint8_t* dst) { memcpy(dst, rgb, n); }))
+  if (ingest_upload<uint8_t>(m, m->in_rgb, rgb, n, [&](uint8_t* dst) { memcpy(dst, rgb, n); }))
     return 1;
-  m->rgb_ptr = m->d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
-  m->h2d_bytes += n;
+  m->rgb_ptr = (const uint8_t*) m->in_rgb.d_buf[m->in_rgb.which], m->rgb_rows = rows, m->rgb_cols = cols;
   return 0;
 }
 
@@ -380,13 +399,12 @@ int mrh_set_rgb_f32(mrh_map* m, const float* rgb, int rows, int cols) {
   if (!rgb || rows <= 0 || cols <= 0)
     return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
   const size_t n = (size_t) rows * cols * 3;
-  if (stage_upload(m, m->h_rgb, m->h_rgb_cap, m->ev_rgb, &m->rgb_which, &m->d_rgb, &m->d_rgb_cap, n, [&](uint8_t* dst) {
+  if (ingest_upload<uint8_t>(m, m->in_rgb, nullptr, n, [&](uint8_t* dst) {
         for (size_t i = 0; i < n; ++i)
           dst[i] = (uint8_t) rgb[i];
       }))
     return 1;
-  m->rgb_ptr = m->d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
-  m->h2d_bytes += n;
+  m->rgb_ptr = (const uint8_t*) m->in_rgb.d_buf[m->in_rgb.which], m->rgb_rows = rows, m->rgb_cols = cols;
   return 0;
 }
 
@@ -394,6 +412,7 @@ int mrh_set_depth_device(mrh_map* m, const float* d_depth, int rows, int cols) {
   if (!m || !d_depth || rows <= 0 || cols <= 0)
     return fail("mrh_set_depth_device: bad argument");
   m->depth_ptr = d_depth, m->depth_rows = rows, m->depth_cols = cols;
+  m->in_depth.active = false;
   return 0;
 }
 
@@ -401,6 +420,7 @@ int mrh_set_rgb_device(mrh_map* m, const uint8_t* d_rgb, int rows, int cols) {
   if (!m || !d_rgb || rows <= 0 || cols <= 0)
     return fail("mrh_set_rgb_device: bad argument");
   m->rgb_ptr = d_rgb, m->rgb_rows = rows, m->rgb_cols = cols;
+  m->in_rgb.active = false;
   return 0;
 }
 
@@ -415,11 +435,10 @@ int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* norma
   }
   if (!m->p.projective_sdf)
     return fail("mrh_set_points: only projective_sdf=True is implemented (every shipped runner uses it)");
-  if (stage_upload(m, m->h_points, m->h_points_cap, m->ev_points, &m->points_which, &m->d_points, &m->d_points_cap, n * 3, [&](float* dst) { memcpy(dst, points, sizeof(float) * n * 3); }))
+  if (ingest_upload<float>(m, m->in_points, points, n * 3, [&](float* dst) { memcpy(dst, points, sizeof(float) * n * 3); }))
     return 1;
+  m->d_points = (float*) m->in_points.d_buf[m->in_points.which];
   m->n_points = n;
-  m->h_points_last = m->h_points[m->points_which];
-  m->h2d_bytes += sizeof(float) * 3 * n;
   return 0;
 }
 
@@ -431,12 +450,19 @@ int mrh_compute(mrh_map* m) {
       return fail("mrh_compute: depth %dx%d / rgb %dx%d do not match the camera %ux%u", m->depth_rows, m->depth_cols, m->rgb_rows, m->rgb_cols, m->cam.rows, m->cam.cols);
   }
   refresh_map_params(m);
+  Ingest* used[3] = {rgbd ? &m->in_depth : nullptr, rgbd ? &m->in_rgb : nullptr, m->n_points ? &m->in_points : nullptr};
+  for (Ingest* in : used)
+    if (in && in->active)
+      CK(cudaStreamWaitEvent(m->stream, in->copied[in->which], 0));
   CK(cudaEventRecord(m->ev0, m->stream));
   if (rgbd && integrate_rgbd(m))
     return 1;
   if (m->n_points && integrate_points(m))
     return 1;
   CK(cudaEventRecord(m->ev1, m->stream));
+  for (Ingest* in : used)
+    if (in && in->active)
+      CK(cudaEventRecord(in->consumed[in->which], m->stream));
   return 0;
 }
 

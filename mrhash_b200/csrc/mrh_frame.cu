@@ -10,6 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "mrh_host.h"
+#include "mrh_fast.cuh"
 #include "mrh_kernels.cuh"
 #include "mrh_points.cuh"
 #include "mrh_var.cuh"
@@ -144,25 +145,46 @@ int integrate_rgbd(mrh_map* m) {
     if (prof)
       cudaEventRecord(m->ev_k[i], s);
   };
-  if (c.var && top_up_low_heap(c))
-    return 1;
-  const dim3 grid_alloc((k.cols + 31) / 32, (k.rows + 7) / 8);
-  mark(0);
-  k_alloc_rgbd<<<grid_alloc, 256, 0, s>>>(d, f, k, m->depth_ptr);
-  CKL();
-  mark(1);
-  k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 1);
-  CKL();
-  mark(2);
-  m->launches += 2;
   const bool fused_gc = c.gc && !c.starve && !c.var;
-  if (fused_gc)
-    k_integrate<true><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
-  else
+  if (!c.var) {
+    // two-launch frame (mrh_fast.cuh)
+    if (!m->counters_clean) {
+      k_zero_frame_counters<<<1, 1, 0, s>>>(d, f.live_cur ^ 1u);
+      m->launches += 1;
+    }
+    const uint32_t tiles_x = (k.cols + 31) / 32, tiles_y = (k.rows + 7) / 8;
+    const uint32_t n_vis_ctas = (uint32_t) m->num_sms;
+    const int rearm           = c.starve ? 0 : 1;
+    mark(0);
+    k_front<<<tiles_x * tiles_y + n_vis_ctas, 256, 0, s>>>(d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
+    CKL();
+    mark(1);
+    mark(2);
+    if (fused_gc)
+      k_integrate8<true><<<m->num_sms * 16, 64, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+    else
+      k_integrate8<false><<<m->num_sms * 16, 64, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+    CKL();
+    mark(3);
+    m->launches += 2;
+    m->counters_clean = rearm != 0;
+  } else {
+    if (top_up_low_heap(c))
+      return 1;
+    const dim3 grid_alloc((k.cols + 31) / 32, (k.rows + 7) / 8);
+    mark(0);
+    k_alloc_rgbd<<<grid_alloc, 256, 0, s>>>(d, f, k, m->depth_ptr);
+    CKL();
+    mark(1);
+    k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 1);
+    CKL();
+    mark(2);
     k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
-  CKL();
-  mark(3);
-  m->launches += 1;
+    CKL();
+    mark(3);
+    m->launches += 3;
+    m->counters_clean = false;
+  }
   bool swapped_twice = false;
   FrameDev f2        = f;
   if (c.var) {
@@ -283,6 +305,7 @@ int integrate_points(mrh_map* m) {
   }
   if (c.gc && gc_tail(c, f2))
     return 1;
+  m->counters_clean = false;
   end_frame(c, swapped_twice);
   return 0;
 }

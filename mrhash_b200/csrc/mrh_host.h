@@ -70,6 +70,18 @@ namespace mrh {
 
   int fail(const char* fmt, ...);
 
+  // one double-buffered host->device channel (depth, colour or points)
+  struct Ingest {
+    void* d_buf[2]{};
+    size_t d_cap[2]{};
+    void* h_buf[2]{}; // pinned staging, used when the caller's memory is pageable
+    size_t h_cap[2]{};
+    cudaEvent_t copied[2]{};   // on the copy stream, after the H2D into d_buf[w]
+    cudaEvent_t consumed[2]{}; // on the compute stream, after the last frame that read d_buf[w]
+    int which   = 0;
+    bool active = false; // d_buf[which] holds the current frame's data
+  };
+
 } // namespace mrh
 
 struct mrh_map {
@@ -86,33 +98,19 @@ struct mrh_map {
   uint64_t num_sdf_blocks = 0, hash_num_buckets = 0, max_num_triangles = 0, max_stream_blocks = 0;
   size_t zbuf_cap = 0;
 
-  // ingest (pinned, double buffered)
-  float* h_depth[2]{};
-  size_t h_depth_cap[2]{};
-  cudaEvent_t ev_depth[2]{};
-  int depth_which = 0;
-  uint8_t* h_rgb[2]{};
-  size_t h_rgb_cap[2]{};
-  cudaEvent_t ev_rgb[2]{};
-  int rgb_which = 0;
-  float* h_points[2]{};
-  size_t h_points_cap[2]{};
-  cudaEvent_t ev_points[2]{};
-  int points_which     = 0;
-  float* h_points_last = nullptr;
-  float* d_depth       = nullptr;
-  size_t d_depth_cap   = 0;
-  uint8_t* d_rgb       = nullptr;
-  size_t d_rgb_cap     = 0;
-  float* d_points      = nullptr;
-  size_t d_points_cap  = 0;
+  // ingest: copies run on their own stream into double-buffered device images, so the transfer of
+  // frame k+1 overlaps the kernels of frame k (mrh_capi.cu: struct use in ingest_upload)
+  cudaStream_t copy_stream = nullptr;
+  mrh::Ingest in_depth, in_rgb, in_points;
   const float* depth_ptr = nullptr;
   const uint8_t* rgb_ptr = nullptr;
   int depth_rows = 0, depth_cols = 0, rgb_rows = 0, rgb_cols = 0;
   size_t n_points = 0;
+  float* d_points = nullptr;
 
   uint32_t frame_index = 0; // num_integrated_frames_ (voxel_data_structures.cpp:106)
   uint32_t live_cur    = 0;
+  bool counters_clean  = true; // live_count[live_cur ^ 1] and vis_count are already zero (fast RGB-D path precondition)
   uint64_t frames_total = 0;
   uint64_t launches     = 0;
   uint64_t h2d_bytes    = 0;

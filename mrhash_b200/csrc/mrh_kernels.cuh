@@ -102,28 +102,26 @@ __global__ void __launch_bounds__(256) k_alloc_rgbd(MapDev m, FrameDev f, Camera
 // ---------------------------------------------------------------------------------------------
 // k_visible: O(live) frustum pass over the dense live list (no full-table scan).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_visible(MapDev m, FrameDev f, CameraDev cam, int use_frustum) {
-  __shared__ PoseDev pose;
-  if (threadIdx.x == 0)
-    load_pose(f, pose);
-  __syncthreads();
+// Visibility pass over the input live list of the frame: frustum test (isSDFBlockInCameraFrustumApprox,
+// voxel_data_structures.cu:66-77), compaction of the live list, emission of the visible list.
+// cta / n_ctas: the caller's position in the set of CTAs that share this work.
+__device__ __forceinline__ void visible_pass(const MapDev& m, uint32_t cur, const CameraDev& cam, const PoseDev& pose, int use_frustum, uint32_t cta, uint32_t n_ctas) {
   const unsigned full  = 0xFFFFFFFFu;
   const int lane       = threadIdx.x & 31;
-  const uint32_t cur   = f.live_cur;
   const uint32_t n     = m.ctr->live_count[cur];
-  const uint32_t* in   = m.live[cur];
-  uint32_t* out        = m.live[cur ^ 1u];
+  const LiveEntry* in  = m.live[cur];
+  LiveEntry* out       = m.live[cur ^ 1u];
   const uint32_t n_pad = (n + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-    uint32_t slot            = i < n ? in[i] : kInvalid;
-    unsigned long long key   = kEmpty;
-    if (slot != kInvalid)
-      key = m.keys[slot];
-    const bool alive = slot != kInvalid && key < kNoKey;
-    i3 b             = {0, 0, 0};
-    bool vis         = false;
+  for (uint32_t i = cta * blockDim.x + threadIdx.x; i < n_pad; i += n_ctas * blockDim.x) {
+    LiveEntry le = {kEmpty, kInvalid, 0u};
+    if (i < n)
+      le = in[i];
+    const uint32_t slot = le.slot;
+    const bool alive    = slot != kInvalid;
+    i3 b                = {0, 0, 0};
+    bool vis            = false;
     if (alive) {
-      b   = unpack_key(key);
+      b   = unpack_key(le.key);
       vis = use_frustum ? block_in_frustum(cam, pose, b, m.voxel_size) : true;
     }
     const unsigned am = __ballot_sync(full, alive);
@@ -140,11 +138,11 @@ __global__ void __launch_bounds__(256) k_visible(MapDev m, FrameDev f, CameraDev
     const unsigned lt    = (1u << lane) - 1u;
     const uint32_t my_li = abase + __popc(am & lt);
     if (alive)
-      out[my_li] = slot;
+      out[my_li] = le;
     if (vis) {
       VisEntry e;
       e.x = b.x, e.y = b.y, e.z = b.z;
-      e.val      = m.vals[slot];
+      e.val      = le.val;
       e.slot     = slot;
       e.live_idx = my_li;
       e.pad0 = e.pad1 = 0;
@@ -153,13 +151,21 @@ __global__ void __launch_bounds__(256) k_visible(MapDev m, FrameDev f, CameraDev
   }
 }
 
+__global__ void __launch_bounds__(256) k_visible(MapDev m, FrameDev f, CameraDev cam, int use_frustum) {
+  __shared__ PoseDev pose;
+  if (threadIdx.x == 0)
+    load_pose(f, pose);
+  __syncthreads();
+  visible_pass(m, f.live_cur, cam, pose, use_frustum, blockIdx.x, gridDim.x);
+}
+
 // Remove a block from the map: tombstone its key, return its pool block to the free stack
 // (appendHeapHigh :52-56), drop it from the live list. Called by one thread.
 __device__ __forceinline__ void free_block(const MapDev& m, uint32_t live_cur, const VisEntry& e) {
   atomicExch(m.keys + e.slot, kTomb);
   const int addr   = atomicAdd(&m.ctr->heap_counter, 1);
   m.heap[addr + 1] = e.val & 0x7FFFFFFFu;
-  m.live[live_cur ^ 1u][e.live_idx] = kInvalid;
+  m.live[live_cur ^ 1u][e.live_idx].slot = kInvalid;
 }
 
 __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uint32_t max_w) {

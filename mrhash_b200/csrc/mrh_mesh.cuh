@@ -295,13 +295,11 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_live = m.ctr->live_count[live_cur];
   for (uint32_t li = blockIdx.x; li < n_live; li += gridDim.x) {
-    const uint32_t slot = m.live[live_cur][li];
-    if (slot == kInvalid)
+    const LiveEntry le = m.live[live_cur][li];
+    if (le.slot == kInvalid)
       continue;
-    const unsigned long long key = m.keys[slot];
-    if (key >= kNoKey)
-      continue;
-    const uint32_t val = m.vals[slot];
+    const unsigned long long key = le.key;
+    const uint32_t val           = le.val;
     const i3 b         = unpack_key(key);
     const int res      = (int) (val >> 31);
     if (tid == 0)

@@ -34,13 +34,11 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   const int tid    = threadIdx.x;
   const uint32_t n = min(m.ctr->live_count[live_cur], first + max_out);
   for (uint32_t i = first + blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t slot = m.live[live_cur][i];
-    if (slot == kInvalid)
+    const LiveEntry le = m.live[live_cur][i];
+    if (le.slot == kInvalid)
       continue;
-    const unsigned long long key = m.keys[slot];
-    if (key >= kNoKey)
-      continue;
-    const uint32_t val = m.vals[slot];
+    const unsigned long long key = le.key;
+    const uint32_t val           = le.val;
     if (tid == 0)
       s_out = atomicAdd(out_count, 1u);
     __syncthreads();

@@ -27,7 +27,9 @@ __device__ __forceinline__ int table_find(const MapDev& m, i3 b) {
     bool has_empty = false;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      const uint32_t bkt       = (h + 2u * w + half) % m.num_buckets;
+      uint32_t bkt = h + 2u * w + half;
+      if (bkt >= m.num_buckets)
+        bkt %= m.num_buckets;
       const ulonglong2* row    = reinterpret_cast<const ulonglong2*>(m.keys + (size_t) bkt * kBucketSlots);
 #pragma unroll
       for (int i = 0; i < kBucketSlots / 2; ++i) {
@@ -53,7 +55,9 @@ __device__ __forceinline__ int table_find(const MapDev& m, i3 b) {
 // key can never both insert it and no bucket mutex / host retry loop is needed.
 // Returns (to every lane) the pool value of the block when this call inserted it, kInvalid otherwise.
 // resolution 1 takes a 64-voxel sub-slot from the low heap (reallocBlock, voxel_data_structures.cu:626-755).
-template <bool FRUSTUM_TEST>
+// DIRECT_VIS: the new block goes straight to the frame's output live list and visible list (it has
+// just passed the frustum test); otherwise it is appended to the input live list live[live_cur].
+template <bool FRUSTUM_TEST, bool DIRECT_VIS = false>
 __device__ __forceinline__ uint32_t warp_insert(const MapDev& m, const CameraDev& cam, const PoseDev& pose, uint32_t live_cur, i3 b, int lane, int resolution = 0) {
   const unsigned full = 0xFFFFFFFFu;
   if (!key_in_range(b)) {
@@ -73,7 +77,9 @@ __device__ __forceinline__ uint32_t warp_insert(const MapDev& m, const CameraDev
     bool found = false, end = false;
 #pragma unroll 1
     for (int w = 0; w < kMaxWindows && !end; ++w) {
-      const uint32_t bkt  = (h + 2u * w + (lane >> 4)) % m.num_buckets;
+      uint32_t bkt = h + 2u * w + (lane >> 4);
+      if (bkt >= m.num_buckets)
+        bkt %= m.num_buckets;
       const uint32_t slot = bkt * kBucketSlots + (lane & 15);
       const unsigned long long k = attempt == 0 ? m.keys[slot] : ld_cg_u64(m.keys + slot);
       if (__ballot_sync(full, k == key)) {
@@ -124,9 +130,16 @@ __device__ __forceinline__ uint32_t warp_insert(const MapDev& m, const CameraDev
             m.stats[val] = {3.40282346638528859812e+38f, 0u};
           }
           m.vals[free_slot]  = val;
-          const uint32_t cur = live_cur;
+          const uint32_t cur = DIRECT_VIS ? (live_cur ^ 1u) : live_cur;
           const uint32_t li  = atomicAdd(&m.ctr->live_count[cur], 1u);
-          m.live[cur][li]    = (uint32_t) free_slot;
+          m.live[cur][li]    = {key, (uint32_t) free_slot, val};
+          if (DIRECT_VIS) {
+            const uint32_t vi = atomicAdd(&m.ctr->vis_count, 1u);
+            VisEntry e;
+            e.x = b.x, e.y = b.y, e.z = b.z;
+            e.val = val, e.slot = (uint32_t) free_slot, e.live_idx = li, e.pad0 = e.pad1 = 0;
+            m.vis[vi] = e;
+          }
           atomicAdd(&m.ctr->blocks_new, 1ull);
         }
       }

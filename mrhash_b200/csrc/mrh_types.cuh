@@ -13,7 +13,7 @@
 //                        untouched blocks is answered without re-reading their payload
 //   heap[num_blocks]     free stack of pool indices (heap[i] = N-1-i initially, voxel_data_structures.cpp:58-69)
 //   heap_low[8*num_blocks] free stack of 64-voxel sub-slot indices (allocateMemoryLow :860-871)
-//   live[2][2*num_blocks] dense list of occupied table slots (double buffered, compacted per frame)
+//   live[2][2*num_blocks] dense list of live blocks {key, slot, val} (double buffered, compacted per frame)
 //   vis[2*num_blocks]    per-frame list of in-frustum blocks (the reference's compact hash table)
 #pragma once
 #include "mrh_math.cuh"
@@ -39,7 +39,7 @@ struct Counters {
   uint32_t n_reintegrate;
   uint32_t n_updates;    // point-cloud path: records emitted this frame
   uint32_t carve_request; // variance path: pool blocks to split into sub-slots this frame
-  uint32_t pad1;
+  uint32_t done_ctas;     // k_integrate: CTAs that have finished (the last one re-arms the frame counters)
   // per-run totals (read back on demand)
   unsigned long long rays_valid;
   unsigned long long blocks_new;
@@ -58,6 +58,13 @@ struct Counters {
 struct BlockStats {
   float min_abs_sdf; // FLT_MAX when no voxel has weight > 0
   uint32_t max_weight;
+};
+
+// entry of the dense live list: everything the visibility pass needs, so it never touches the table
+struct __align__(16) LiveEntry {
+  unsigned long long key;
+  uint32_t slot; // kInvalid = removed since the list was built
+  uint32_t val;
 };
 
 struct __align__(16) VisEntry {
@@ -99,7 +106,7 @@ struct MapDev {
   uint8_t* pool;
   uint8_t* carved; // 1 = pool block split into 8 resolution-1 sub-slots
   BlockStats* stats;
-  uint32_t* live[2];
+  LiveEntry* live[2];
   VisEntry* vis;
   VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
   unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(64) k_check_var(MapDev m, FrameDev f) {
           atomicExch(m.keys + e.slot, kTomb);
           const int addr   = atomicAdd(&m.ctr->heap_counter, 1);
           m.heap[addr + 1] = e.val;
-          m.live[f.live_cur ^ 1u][e.live_idx] = kInvalid;
+          m.live[f.live_cur ^ 1u][e.live_idx].slot = kInvalid;
           m.stats[e.val]   = {3.40282346638528859812e+38f, 0u};
           const uint32_t q = atomicAdd(&m.ctr->n_realloc, 1u);
           VisEntry r       = e;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(128) k_gc_low(MapDev m, FrameDev f) {
       atomicExch(m.keys + e.slot, kTomb);
       const int addr       = atomicAdd(&m.ctr->heap_low_counter, 1); // appendHeapLow (:58-62)
       m.heap_low[addr + 1] = low;
-      m.live[f.live_cur ^ 1u][e.live_idx] = kInvalid;
+      m.live[f.live_cur ^ 1u][e.live_idx].slot = kInvalid;
       atomicAdd(&m.ctr->blocks_freed, 1ull);
       atomicAdd(&m.ctr->low_live, (unsigned long long) -1ll);
     }
