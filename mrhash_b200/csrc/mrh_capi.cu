@@ -75,6 +75,7 @@ static int alloc_map(mrh_map* m) {
   d.num_blocks  = (uint32_t) N;
   d.num_buckets = (uint32_t) NB;
   d.capacity    = (uint32_t) (NB * kBucketSlots);
+  d.bucket_magic = (uint32_t) std::min<uint64_t>((1ull << 32) / NB, 0xFFFFFFFFull);
   CK(cudaMalloc(&d.keys, sizeof(unsigned long long) * d.capacity));
   CK(cudaMalloc(&d.vals, sizeof(uint32_t) * d.capacity));
   CK(cudaMalloc(&d.heap, sizeof(uint32_t) * N));
@@ -265,6 +266,11 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   m->num_sms = prop.multiProcessorCount;
+  {
+    const char* e      = getenv("MRH_INTEGRATE_CTAS_PER_SM");
+    const int per_sm   = e ? std::max(1, atoi(e)) : 9;
+    m->integrate_grid = m->num_sms * per_sm;
+  }
 
   // sizing: geowrapper.cpp:37-54 with params.h:33-37 ratios, in 64-bit arithmetic
   size_t free_b = 0, total_b = 0;

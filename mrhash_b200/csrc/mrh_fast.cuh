@@ -16,7 +16,7 @@
 
 namespace mrh {
 
-constexpr int kTileKeys = 128; // per-CTA cache of block keys already resolved this frame
+constexpr int kTileSet = 256; // per-tile set of block keys (one tile = 32 x 8 rays)
 
 __device__ __forceinline__ uint32_t key_hash(unsigned long long k) {
   k ^= k >> 29;
@@ -24,13 +24,41 @@ __device__ __forceinline__ uint32_t key_hash(unsigned long long k) {
   return (uint32_t) (k >> 40);
 }
 
+// insert-if-absent into the tile's shared-memory key set; false = no room within the probe limit
+__device__ __forceinline__ bool tile_set_insert(unsigned long long* s_set, unsigned long long key) {
+  const uint32_t h = key_hash(key);
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) {
+    unsigned long long* cell   = s_set + ((h + j) & (kTileSet - 1));
+    const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(cell);
+    if (c == key)
+      return true;
+    if (c == kNoKey) {
+      const unsigned long long old = atomicCAS(cell, kNoKey, key);
+      if (old == kNoKey || old == key)
+        return true;
+    }
+  }
+  return false;
+}
+
+// Allocation role, two phases per tile:
+//   1. every ray walks its block DDA and drops the visited keys into a shared-memory set (the 256
+//      rays of a tile visit only ~10-20 distinct blocks);
+//   2. the distinct keys are handed out to the 8 warps, ONE warp-cooperative table insert each.
+// If the set fills up (long grazing rays), the walk pauses, phase 2 drains the set, and the walk
+// resumes: any ray length is handled.
 __global__ void __launch_bounds__(256) k_front(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, uint32_t tiles_x, uint32_t n_vis_ctas) {
   __shared__ PoseDev pose;
-  __shared__ unsigned long long s_keys[kTileKeys];
-  if (threadIdx.x == 0)
+  __shared__ unsigned long long s_set[kTileSet];
+  __shared__ unsigned long long s_list[kTileSet];
+  __shared__ uint32_t s_n;
+  __shared__ int s_full;
+  if (threadIdx.x == 0) {
     load_pose(f, pose);
-  if (threadIdx.x < kTileKeys)
-    s_keys[threadIdx.x] = kNoKey;
+    s_n = 0, s_full = 0;
+  }
+  s_set[threadIdx.x] = kNoKey;
   __syncthreads();
   if (blockIdx.x < n_vis_ctas) { // scheduled first: the visibility role is a pure latency chain
     visible_pass(m, f.live_cur, cam, pose, 1, blockIdx.x, n_vis_ctas);
@@ -63,59 +91,59 @@ __global__ void __launch_bounds__(256) k_front(MapDev m, FrameDev f, CameraDev c
   if (lane == 0 && n_rays)
     atomicAdd(&m.ctr->rays_valid, (unsigned long long) n_rays);
   int iter = 0;
-  while (__any_sync(full, active)) {
-    unsigned long long key = kNoKey;
-    bool want              = false;
-    uint32_t hk            = 0;
-    if (active) {
-      if (key_in_range(dda.cur)) {
-        key = pack_key(dda.cur);
-        hk  = key_hash(key);
-        // resolved already by some warp of this tile (present, inserted, or outside the frustum)?
-        want = true;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned long long c = s_keys[(hk + j) & (kTileKeys - 1)];
-          if (c == key) {
-            want = false;
-            break;
-          }
-          if (c == kNoKey)
-            break;
-        }
-      } else {
-        atomicAdd(&m.ctr->dropped_table, 1ull);
+  bool more;
+  do {
+    // ---- phase 1: walk, collect keys ----
+    while (__any_sync(full, active)) {
+      if (__shfl_sync(full, *reinterpret_cast<volatile int*>(&s_full), 0))
+        break;
+      unsigned long long key = kNoKey;
+      if (active) {
+        if (key_in_range(dda.cur))
+          key = pack_key(dda.cur);
+        else
+          atomicAdd(&m.ctr->dropped_table, 1ull);
       }
-    }
-    // one leader per distinct unresolved key of the warp
-    const unsigned peers = __match_any_sync(full, want ? key : kNoKey);
-    const bool leader    = want && (lane == __ffs(peers) - 1);
-    unsigned todo        = __ballot_sync(full, leader);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const i3 b = {__shfl_sync(full, dda.cur.x, src), __shfl_sync(full, dda.cur.y, src), __shfl_sync(full, dda.cur.z, src)};
-      warp_insert<true, true>(m, cam, pose, f.live_cur, b, lane);
-      if (lane == src) {
-        // remember the outcome (first free cell of the short probe sequence; a lost race between
-        // warps only costs a repeated probe)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t c = (hk + j) & (kTileKeys - 1);
-          if (s_keys[c] == kNoKey) {
-            s_keys[c] = key;
-            break;
-          }
+      // one lane per distinct key of the warp talks to the set
+      const unsigned peers = __match_any_sync(full, key);
+      const int leader     = __ffs(peers) - 1;
+      int placed           = 1;
+      if (key != kNoKey && lane == leader)
+        placed = tile_set_insert(s_set, key) ? 1 : 0;
+      placed = __shfl_sync(full, placed, leader);
+      if (active) {
+        if (placed) {
+          active = dda.advance();
+          if (++iter >= kMaxDDA)
+            active = false;
+        } else {
+          s_full = 1; // keep the DDA where it is: this key is retried after the set has been drained
         }
       }
     }
-    __syncwarp();
-    if (active) {
-      active = dda.advance();
-      if (++iter >= kMaxDDA)
-        active = false;
+    __syncthreads();
+    // ---- phase 2: one table insert per distinct key ----
+    {
+      const unsigned long long k = s_set[threadIdx.x];
+      const unsigned has         = __ballot_sync(full, k != kNoKey);
+      uint32_t base              = 0;
+      if (lane == 0 && has)
+        base = atomicAdd(&s_n, (uint32_t) __popc(has));
+      base = __shfl_sync(full, base, 0);
+      if (k != kNoKey)
+        s_list[base + __popc(has & ((1u << lane) - 1u))] = k;
     }
-  }
+    __syncthreads();
+    const uint32_t n_keys = s_n;
+    for (uint32_t i = warp; i < n_keys; i += 8)
+      warp_insert<true, true>(m, cam, pose, f.live_cur, unpack_key(s_list[i]), lane);
+    more = s_full != 0;
+    __syncthreads();
+    s_set[threadIdx.x] = kNoKey;
+    if (threadIdx.x == 0)
+      s_n = 0, s_full = 0;
+    __syncthreads();
+  } while (more);
 }
 
 __global__ void k_zero_frame_counters(MapDev m, uint32_t live_out) {

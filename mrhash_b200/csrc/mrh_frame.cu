@@ -161,9 +161,9 @@ int integrate_rgbd(mrh_map* m) {
     mark(1);
     mark(2);
     if (fused_gc)
-      k_integrate8<true><<<m->num_sms * 16, 64, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      k_integrate<true><<<m->integrate_grid, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     else
-      k_integrate8<false><<<m->num_sms * 16, 64, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      k_integrate<false><<<m->integrate_grid, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     CKL();
     mark(3);
     m->launches += 2;
@@ -179,7 +179,7 @@ int integrate_rgbd(mrh_map* m) {
     k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 1);
     CKL();
     mark(2);
-    k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr);
+    k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, 0);
     CKL();
     mark(3);
     m->launches += 3;

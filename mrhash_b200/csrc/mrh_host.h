@@ -88,6 +88,7 @@ struct mrh_map {
   mrh_params p{};
   int device  = 0;
   int num_sms = 148;
+  int integrate_grid = 148 * 8; // CTAs of k_integrate (env MRH_INTEGRATE_CTAS_PER_SM overrides, for tuning)
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mrh::MapDev dev{};

@@ -175,8 +175,10 @@ __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uin
 // ---------------------------------------------------------------------------------------------
 // k_integrate: one CTA (128 threads x 4 consecutive-x voxels) per visible block, persistent.
 // ---------------------------------------------------------------------------------------------
+// rearm: the last CTA to finish zeroes the list counters the next frame's k_front appends to (every
+// CTA has read vis_count by then), so a frame needs no reset kernel.
 template <bool FUSE_GC>
-__global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb) {
+__global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
   __shared__ PoseDev pose;
   __shared__ float s_min[4];
   __shared__ uint32_t s_max[4];
@@ -322,6 +324,15 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
       atomicAdd(&m.ctr->voxels_updated, cta_updated);
     if (blockIdx.x == 0)
       atomicAdd(&m.ctr->blocks_visible, (unsigned long long) n_vis);
+    if (rearm) {
+      __threadfence();
+      const unsigned done = atomicAdd(&m.ctr->done_ctas, 1u) + 1u;
+      if (done == gridDim.x) {
+        m.ctr->live_count[f.live_cur] = 0; // next frame's output list
+        m.ctr->vis_count              = 0;
+        m.ctr->done_ctas              = 0;
+      }
+    }
   }
 }
 

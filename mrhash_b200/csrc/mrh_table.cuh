@@ -14,6 +14,16 @@ __device__ __forceinline__ void load_pose(const FrameDev& f, PoseDev& pose) {
   pose_finish(pose);
 }
 
+// calculateHash without the integer division: q = umulhi(h, floor(2^32 / n)) is floor(h / n) or one
+// less, so one conditional subtraction finishes the remainder.
+__device__ __forceinline__ uint32_t block_hash_fast(const MapDev& m, i3 b) {
+  const uint32_t h = ((uint32_t) b.x * 73856093u) ^ ((uint32_t) b.y * 19349669u) ^ ((uint32_t) b.z * 83492791u);
+  uint32_t r       = h - __umulhi(h, m.bucket_magic) * m.num_buckets;
+  if (r >= m.num_buckets)
+    r -= m.num_buckets;
+  return r;
+}
+
 // Single-thread lookup. Probe order: windows of two buckets starting at the home bucket; a window
 // that holds an EMPTY slot terminates the chain (inserts always take the first free slot in this
 // order and slots never return to EMPTY, so a present key sits before the first EMPTY).
@@ -21,7 +31,7 @@ __device__ __forceinline__ int table_find(const MapDev& m, i3 b) {
   if (!key_in_range(b))
     return -1;
   const unsigned long long key = pack_key(b);
-  const uint32_t h             = block_hash(b, m.num_buckets);
+  const uint32_t h             = block_hash_fast(m, b);
 #pragma unroll 1
   for (int w = 0; w < kMaxWindows; ++w) {
     bool has_empty = false;
@@ -65,7 +75,7 @@ __device__ __forceinline__ uint32_t warp_insert(const MapDev& m, const CameraDev
       atomicAdd(&m.ctr->dropped_table, 1ull);
     return kInvalid;
   }
-  const uint32_t h = block_hash(b, m.num_buckets);
+  const uint32_t h = block_hash_fast(m, b);
   if (h < m.shard_lo || h >= m.shard_hi)
     return kInvalid; // another GPU owns this bucket range
   const unsigned long long key = pack_key(b);

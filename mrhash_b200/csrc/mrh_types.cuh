@@ -98,6 +98,7 @@ struct MapDev {
   int min_weight_threshold;
   int projective;
   uint32_t num_buckets, capacity, num_blocks;
+  uint32_t bucket_magic; // floor(2^32 / num_buckets): block_hash_fast needs no integer division
   uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
   unsigned long long* keys;
   uint32_t* vals;
