@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmrhash_b200.so")
+LIB_PATH = os.environ.get("MRH_LIB", os.path.join(_HERE, "libmrhash_b200.so"))  # MRH_LIB: tuning builds only
 
 
 class Params(C.Structure):

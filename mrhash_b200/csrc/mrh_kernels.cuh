@@ -120,9 +120,10 @@ __device__ __forceinline__ void visible_pass(const MapDev& m, uint32_t cur, cons
     const bool alive    = slot != kInvalid;
     i3 b                = {0, 0, 0};
     bool vis            = false;
+    bool maybe          = true;
     if (alive) {
       b   = unpack_key(le.key);
-      vis = use_frustum ? block_in_frustum(cam, pose, b, m.voxel_size) : true;
+      vis = use_frustum ? block_in_frustum_ex(cam, pose, b, m.voxel_size, maybe) : true;
     }
     const unsigned am = __ballot_sync(full, alive);
     const unsigned vm = __ballot_sync(full, vis);
@@ -145,7 +146,8 @@ __device__ __forceinline__ void visible_pass(const MapDev& m, uint32_t cur, cons
       e.val      = le.val;
       e.slot     = slot;
       e.live_idx = my_li;
-      e.pad0 = e.pad1 = 0;
+      e.maybe_in_image = maybe ? 1u : 0u;
+      e.pad1           = 0;
       m.vis[vbase + __popc(vm & lt)] = e;
     }
   }
@@ -197,16 +199,16 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
     if (e.val & 0x80000000u)
       continue; // resolution-1 blocks are fused by k_integrate_lowres
     // ---- pass 1: projection + depth test, registers only ----
-    float sdf_new[4];
-    uint32_t pix[4];
-    unsigned ok = 0;
+    float sdf_new[4] = {0.f, 0.f, 0.f, 0.f};
+    uint32_t pix[4]  = {0u, 0u, 0u, 0u};
+    unsigned ok      = 0;
+    if (e.maybe_in_image) { // else: no voxel of this block can project into the image (k_visible)
     const f3 pf_yz = {0.f, fmul(i2f(e.y * kBlockSide + ly), m.voxel_size), fmul(i2f(e.z * kBlockSide + lz), m.voxel_size)};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const f3 pf = {fmul(i2f(e.x * kBlockSide + lx0 + j), m.voxel_size), pf_yz.y, pf_yz.z};
       const f3 pc = se3_mul(pose.Ri, pose.ti, pf);
       int row, col;
-      sdf_new[j] = 0.f, pix[j] = 0;
       if (project_point(cam, pc, row, col)) {
         const uint32_t p = (uint32_t) row * cam.cols + (uint32_t) col;
         const float d    = cloud_depth(cam, (uint32_t) row, (uint32_t) col, __ldg(depth + p));
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
         }
       }
     }
-    const int any = __syncthreads_or((int) ok);
+    }
+    const int any = e.maybe_in_image ? __syncthreads_or((int) ok) : 0;
     float min_abs  = 3.40282346638528859812e+38f;
     uint32_t max_w = 0, n_upd = 0;
     uint8_t* base  = m.pool + (size_t) e.val * kBlockBytes;

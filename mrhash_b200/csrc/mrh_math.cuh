@@ -12,6 +12,7 @@
 //   trunc + scale*z    -> fma(scale, z, trunc)          voxel_hash_utils.cuh:184-187
 //   k*size - 0.5*size  -> fma(k, size, -(0.5*size))     voxel_data_structures.cu:797
 #pragma once
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -184,6 +185,31 @@ __device__ __forceinline__ bool block_in_frustum(const CameraDev& c, const PoseD
     if (block_corner_in_frustum(c, pose, b, k, size))
       return true;
   return false;
+}
+
+// Frustum test of a block plus a conservative "can any voxel of it land inside the image?" answer.
+// For the pinhole model the projection maps the box spanned by the block's voxel centres (all in
+// front of the camera) onto the convex hull of its 8 projected corners, so if every corner falls
+// at least 3 pixels outside one image edge no voxel can pass projectPoint (3 px absorbs float
+// rounding and the int(x + 0.5) truncation toward zero). Any corner with an invalid depth, or the
+// spherical model, answers "maybe". Used to skip the per-voxel pass of such blocks.
+__device__ __forceinline__ bool block_in_frustum_ex(const CameraDev& c, const PoseDev& pose, i3 b, float size, bool& maybe_in_image) {
+  bool in_frustum = false, all_valid = c.model == 0;
+  int rmin = INT_MAX, rmax = INT_MIN, qmin = INT_MAX, qmax = INT_MIN;
+#pragma unroll 1
+  for (int k = 0; k < 8; ++k) {
+    const int ox = (k & 4) ? 7 : 0, oy = (k & 2) ? 7 : 0, oz = (k & 1) ? 7 : 0;
+    const f3 w   = {fmul(i2f(b.x * kBlockSide + ox), size), fmul(i2f(b.y * kBlockSide + oy), size), fmul(i2f(b.z * kBlockSide + oz), size)};
+    int r, q;
+    if (project_rc(c, se3_mul(pose.Ri, pose.ti, w), r, q)) {
+      in_frustum |= r >= -c.row_thr && q >= -c.col_thr && r < (int) (c.rows + (uint32_t) c.row_thr) && q < (int) (c.cols + (uint32_t) c.col_thr);
+      rmin = min(rmin, r), rmax = max(rmax, r), qmin = min(qmin, q), qmax = max(qmax, q);
+    } else {
+      all_valid = false;
+    }
+  }
+  maybe_in_image = !all_valid || !(rmax <= -3 || qmax <= -3 || rmin >= (int) c.rows + 3 || qmin >= (int) c.cols + 3);
+  return in_frustum;
 }
 
 // calculateHash (voxel_data_structures.cu:151-160)

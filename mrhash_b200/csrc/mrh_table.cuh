@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t warp_insert(const MapDev& m, const CameraDev
             const uint32_t vi = atomicAdd(&m.ctr->vis_count, 1u);
             VisEntry e;
             e.x = b.x, e.y = b.y, e.z = b.z;
-            e.val = val, e.slot = (uint32_t) free_slot, e.live_idx = li, e.pad0 = e.pad1 = 0;
+            e.val = val, e.slot = (uint32_t) free_slot, e.live_idx = li, e.maybe_in_image = 1u, e.pad1 = 0;
             m.vis[vi] = e;
           }
           atomicAdd(&m.ctr->blocks_new, 1ull);

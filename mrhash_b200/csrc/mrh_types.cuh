@@ -72,7 +72,8 @@ struct __align__(16) VisEntry {
   uint32_t val;
   uint32_t slot;
   uint32_t live_idx;
-  uint32_t pad0, pad1;
+  uint32_t maybe_in_image; // 0: proven that no voxel of the block projects into the image this frame
+  uint32_t pad1;
 };
 
 // record of a gathered block (same layout as mrh_dump_entry)
