@@ -397,14 +397,18 @@ def main():
     sampler.stop()
 
     peak, peak_src = peaks()
-    names = ["k_alloc_rgbd", "k_visible", "k_integrate"]
-    per_kernel = {names[i]: {"ms_per_launch": kms[i] / max(kn[i], 1), "launches": kn[i]} for i in range(3)}
+    # slot 0 = k_front (ray walk + block insert, with the visibility pass of the live list running in
+    # the same launch), slot 2 = k_integrate (fusion + garbage collection); slot 1 is empty on the
+    # two-launch path
+    names = ["k_front", "k_integrate"]
+    per_kernel = {"k_front": {"ms_per_launch": kms[0] / max(kn[0], 1), "launches": kn[0]}, "k_integrate": {"ms_per_launch": kms[2] / max(kn[2], 1), "launches": kn[2]}}
     # algorithmic bytes per launch: integrate = 24 B per updated voxel (12 read + 12
     # written) + 32 B per visible block record + 7 B per pixel (depth + rgb read once)
     bytes_integrate = (24.0 * stp["voxels_updated"] + 32.0 * stp["blocks_visible"]) / Kp + 7.0 * P
-    bytes_alloc = 4.0 * P + 8.0 * 16 * stp["blocks_new"] / Kp  # depth read once + one bucket row per new block
-    bytes_visible = (4.0 + 8.0 + 4.0) * stp["live_blocks"] + 32.0 * stp["blocks_visible"] / Kp
-    algo = {"k_integrate": bytes_integrate, "k_alloc_rgbd": bytes_alloc, "k_visible": bytes_visible}
+    # front = depth read once + one 128 B bucket line per new block + 16 B per live entry read and
+    # rewritten + one 32 B record per visible block
+    bytes_front = 4.0 * P + 128.0 * stp["blocks_new"] / Kp + 32.0 * stp["live_blocks"] + 32.0 * stp["blocks_visible"] / Kp
+    algo = {"k_integrate": bytes_integrate, "k_front": bytes_front}
     dom = max(names, key=lambda k: per_kernel[k]["ms_per_launch"])
     achieved = algo[dom] / (per_kernel[dom]["ms_per_launch"] * 1e-3) / 1e9 if per_kernel[dom]["ms_per_launch"] > 0 else 0.0
     traffic = None
@@ -448,6 +452,7 @@ def main():
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
+            "roofline_integrate": {"bound": "hbm", "kernel": "k_integrate", "achieved": algo["k_integrate"] / (per_kernel["k_integrate"]["ms_per_launch"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo["k_integrate"] / (per_kernel["k_integrate"]["ms_per_launch"] * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": algo["k_integrate"]},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
             "kernels": per_kernel,
             "frame_algorithmic_bytes": 7.0 * P + (24.0 * (b_vis + b_new) + 24.0 * v_upd) / K,

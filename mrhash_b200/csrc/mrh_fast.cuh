@@ -48,7 +48,7 @@ __device__ __forceinline__ bool tile_set_insert(unsigned long long* s_set, unsig
 // If the set fills up (long grazing rays), the walk pauses, phase 2 drains the set, and the walk
 // resumes: any ray length is handled.
 #ifndef MRH_FRONT_MIN_CTAS
-#define MRH_FRONT_MIN_CTAS 4
+#define MRH_FRONT_MIN_CTAS 5
 #endif
 __global__ void __launch_bounds__(256, MRH_FRONT_MIN_CTAS) k_front(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, uint32_t tiles_x, uint32_t n_vis_ctas) {
   __shared__ PoseDev pose;
