@@ -340,6 +340,8 @@ def main():
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
     bcast_d = torch.empty((args.height, args.width), dtype=torch.float32, device=dev) if world > 1 else None
     bcast_c = torch.empty((args.height, args.width, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+    ev_ready, ev_done = torch.cuda.Event(), torch.cuda.Event()
+    ev_done.record(stream)
 
     def step_host(k):
         g.setCurrPose(*poses[k])
@@ -347,15 +349,22 @@ def main():
             g.setDepthImage(depth_np[k])
             g.setRGBImage(rgb_np[k])
         else:
-            # rank 0 ingests the frame from its host buffers; the others receive it over NVLink
-            with torch.cuda.stream(stream):
-                if rank == 0:
-                    bcast_d.copy_(depth_h[k], non_blocking=True)
-                    bcast_c.copy_(rgb_h[k], non_blocking=True)
-                dist.broadcast(bcast_d, 0)
-                dist.broadcast(bcast_c, 0)
+            # rank 0 ingests the frame from its host buffers; the others receive it over NVLink.
+            # The copy + broadcast run on torch's stream; the handle's stream is ordered after them
+            # (and the next broadcast after this frame's kernels) with events only.
+            torch.cuda.current_stream().wait_event(ev_done)
+            if rank == 0:
+                bcast_d.copy_(depth_h[k], non_blocking=True)
+                bcast_c.copy_(rgb_h[k], non_blocking=True)
+            dist.broadcast(bcast_d, 0)
+            dist.broadcast(bcast_c, 0)
+            ev_ready.record()
+            stream.wait_event(ev_ready)
             g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
             g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
+            g.compute()
+            ev_done.record(stream)
+            return g.getStats()
         g.compute()
         return g.getStats()  # D2H read of the frame's counters (synchronises)
 
@@ -374,7 +383,9 @@ def main():
     wall_e2e = time.perf_counter() - t0
     windows[-1][1] = time.time()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_e2e * 1e3))
-    g.close()
+    g_e2e = g  # NCCL enqueued work on this handle's stream: destroy it only after the process group
+    if world == 1:
+        g.close()
 
     # ---------------- roofline pass: per-kernel CUDA-event times, L2 flushed ------------------------
     Kp = min(K, 200)
@@ -462,7 +473,10 @@ def main():
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        g_e2e.close()
 
 
 if __name__ == "__main__":
