@@ -509,6 +509,10 @@ int mrh_get_field(mrh_map* m, const char* name, double* out) {
   else if (n == "SDFVarThreshold") *out = p.sdf_var_threshold;
   else if (n == "VerticesMergingThreshold") *out = p.vertices_merging_threshold;
   else if (n == "MarchingCubesThreshold") *out = p.marching_cubes_threshold;
+  else if (n == "LastMeshStreamMs") *out = m->mesh_ms_stream;
+  else if (n == "LastMeshKernelMs") *out = m->mesh_ms_kernel;
+  else if (n == "LastMeshMergeMs") *out = m->mesh_ms_merge;
+  else if (n == "LastMeshPlyMs") *out = m->mesh_ms_ply;
   else
     return fail("mrh_get_field: unknown field '%s'", name);
   return 0;

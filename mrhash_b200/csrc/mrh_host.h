@@ -2,8 +2,6 @@
 #pragma once
 #include <cstdint>
 #include <string>
-#include <unordered_map>
-#include <unordered_set>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -30,29 +28,57 @@ namespace mrh {
     }
   };
 
-  struct VertexKey {
-    uint64_t a, b, c; // bit patterns of 3 doubles (exact merge) or 3 quantised ints
-    bool operator==(const VertexKey& o) const {
-      return a == o.a && b == o.b && c == o.c;
+  // Open-addressing map from a 3 x u32 key to an int (first-seen index), used by the host mesh
+  // merge: vertex positions (float bit patterns, or quantised cells) and faces (index triples).
+  // Replaces std::unordered_map<Vector3d, int> / std::set<tuple> of mesh_extractor.cpp:156-259.
+  struct Key3Map {
+    struct Cell {
+      uint32_t a, b, c;
+      int32_t value; // -1 = empty
+    };
+    std::vector<Cell> cells;
+    size_t count = 0;
+    void clear() {
+      cells.clear();
+      cells.shrink_to_fit();
+      count = 0;
     }
-  };
-  struct VertexKeyHash {
-    size_t operator()(const VertexKey& k) const {
-      uint64_t h = k.a * 0x9E3779B97F4A7C15ull;
-      h ^= (k.b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
-      h ^= (k.c + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    static size_t mix(uint32_t a, uint32_t b, uint32_t c) {
+      uint64_t h = (uint64_t) a * 0x9E3779B97F4A7C15ull;
+      h ^= (uint64_t) b * 0xC2B2AE3D27D4EB4Full + (h >> 29);
+      h ^= (uint64_t) c * 0x165667B19E3779F9ull + (h << 7);
+      h ^= h >> 32;
       return (size_t) h;
     }
-  };
-  struct FaceKey {
-    int32_t a, b, c;
-    bool operator==(const FaceKey& o) const {
-      return a == o.a && b == o.b && c == o.c;
+    void reserve(size_t n) {
+      size_t cap = 1024;
+      while (cap < 2 * n)
+        cap <<= 1;
+      if (cap <= cells.size())
+        return;
+      std::vector<Cell> old;
+      old.swap(cells);
+      cells.assign(cap, Cell{0, 0, 0, -1});
+      for (const Cell& e : old)
+        if (e.value >= 0)
+          *slot(e.a, e.b, e.c) = e;
     }
-  };
-  struct FaceKeyHash {
-    size_t operator()(const FaceKey& k) const {
-      return (size_t) (((uint64_t) (uint32_t) k.a * 73856093ull) ^ ((uint64_t) (uint32_t) k.b * 19349669ull << 1) ^ ((uint64_t) (uint32_t) k.c * 83492791ull << 2));
+    Cell* slot(uint32_t a, uint32_t b, uint32_t c) {
+      const size_t mask = cells.size() - 1;
+      size_t i          = mix(a, b, c) & mask;
+      while (cells[i].value >= 0 && !(cells[i].a == a && cells[i].b == b && cells[i].c == c))
+        i = (i + 1) & mask;
+      return &cells[i];
+    }
+    // returns the stored value, inserting `value_if_new` first when the key is absent
+    int32_t find_or_insert(uint32_t a, uint32_t b, uint32_t c, int32_t value_if_new, bool& inserted) {
+      Cell* e  = slot(a, b, c);
+      inserted = e->value < 0;
+      if (inserted) {
+        *e = {a, b, c, value_if_new};
+        ++count;
+      }
+      return e->value;
     }
   };
   struct HostMesh {
@@ -60,11 +86,10 @@ namespace mrh {
     std::vector<double> vertices; // V x 3
     std::vector<int32_t> faces;   // F x 3
     std::vector<double> colors;   // V x 3
-    std::unordered_map<VertexKey, int32_t, VertexKeyHash> vertex_map;
-    std::unordered_set<FaceKey, FaceKeyHash> face_set;
+    Key3Map vertex_map, face_map;
     void clear() {
       triangles.clear(), vertices.clear(), faces.clear(), colors.clear();
-      vertex_map.clear(), face_set.clear();
+      vertex_map.clear(), face_map.clear();
     }
   };
 
@@ -137,6 +162,8 @@ struct mrh_map {
   uint32_t* d_tri_count  = nullptr;
   mrh::HostStore store;
   mrh::HostMesh mesh;
+  // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel + D2H, host merge, PLY
+  double mesh_ms_stream = 0, mesh_ms_kernel = 0, mesh_ms_merge = 0, mesh_ms_ply = 0;
 };
 
 namespace mrh {

@@ -2,11 +2,14 @@
 // marching cubes on the device, host merge of the triangle soup (MeshExtractor::processTriangles,
 // mesh_extractor.cpp:9-76,156-259), ASCII PLY.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <string>
+#include <thread>
 
 #include "mrh_host.h"
 #include "mrh_mesh.cuh"
@@ -21,6 +24,9 @@ using namespace mrh;
   } while (0)
 
 namespace {
+  inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
 
   // Streamer::worldToChunks (streamer.cuh:251-260) of a block origin (streamer.cpp:231-233)
   inline void block_chunk(const GatherRecord& r, float size, float ext, int out[3]) {
@@ -38,35 +44,86 @@ namespace {
   // (unique old, new) does.
   void merge_triangles(HostMesh& mesh, const float* tris, size_t n, double eps) {
     const double inv_eps = eps != 0.0 ? 1.0 / eps : 0.0;
+    mesh.vertex_map.reserve(mesh.vertex_map.count + 3 * n);
+    mesh.face_map.reserve(mesh.face_map.count + n);
+    mesh.vertices.reserve(mesh.vertices.size() + 6 * n);
+    mesh.colors.reserve(mesh.colors.size() + 6 * n);
+    mesh.faces.reserve(mesh.faces.size() + 3 * n);
     for (size_t t = 0; t < n; ++t) {
       int32_t idx[3];
       for (int j = 0; j < 3; ++j) {
-        const float* v    = tris + t * 18 + j * 6;
-        const double p[3] = {(double) v[0], (double) v[1], (double) v[2]};
-        VertexKey key;
+        const float* v = tris + t * 18 + j * 6;
+        uint32_t key[3];
         if (eps == 0.0) {
-          memcpy(&key.a, &p[0], 8), memcpy(&key.b, &p[1], 8), memcpy(&key.c, &p[2], 8);
+          // exact merge: byte-wise equality of the doubles == of the floats they were widened from
+          memcpy(key, v, 12);
         } else {
-          key.a = (uint64_t) (int64_t) (int) std::floor(p[0] * inv_eps);
-          key.b = (uint64_t) (int64_t) (int) std::floor(p[1] * inv_eps);
-          key.c = (uint64_t) (int64_t) (int) std::floor(p[2] * inv_eps);
+          for (int k = 0; k < 3; ++k)
+            key[k] = (uint32_t) (int) std::floor((double) v[k] * inv_eps);
         }
-        auto it = mesh.vertex_map.find(key);
-        if (it != mesh.vertex_map.end()) {
-          idx[j] = it->second;
-        } else {
-          idx[j] = (int32_t) (mesh.vertices.size() / 3);
-          mesh.vertex_map.emplace(key, idx[j]);
-          mesh.vertices.insert(mesh.vertices.end(), {p[0], p[1], p[2]});
+        bool inserted;
+        idx[j] = mesh.vertex_map.find_or_insert(key[0], key[1], key[2], (int32_t) (mesh.vertices.size() / 3), inserted);
+        if (inserted) {
+          mesh.vertices.insert(mesh.vertices.end(), {(double) v[0], (double) v[1], (double) v[2]});
           mesh.colors.insert(mesh.colors.end(), {(double) v[3], (double) v[4], (double) v[5]});
         }
       }
       if (idx[0] == idx[1] || idx[0] == idx[2] || idx[1] == idx[2])
         continue; // degenerate after the merge
-      if (!mesh.face_set.insert({idx[0], idx[1], idx[2]}).second)
+      bool inserted;
+      mesh.face_map.find_or_insert((uint32_t) idx[0], (uint32_t) idx[1], (uint32_t) idx[2], 0, inserted);
+      if (!inserted)
         continue; // duplicate face
       mesh.faces.insert(mesh.faces.end(), {idx[0], idx[1], idx[2]});
     }
+  }
+
+  // "%g" is what `ostream << double` prints at the default precision (geowrapper.cpp:194-229);
+  // chunks are formatted in parallel and written in order.
+  void write_mesh_ply(const char* path, const HostMesh& mesh) {
+    const size_t nv = mesh.vertices.size() / 3, nf = mesh.faces.size() / 3;
+    FILE* f = fopen(path, "wb");
+    if (!f) {
+      std::cerr << "GeoWrapper::extractMesh | Failed to open file for writing: " << path << std::endl;
+      return;
+    }
+    fprintf(f, "ply\nformat ascii 1.0\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\n", nv);
+    fprintf(f, "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face %zu\n", nf);
+    fprintf(f, "property list uchar int vertex_indices\nend_header\n");
+    const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto emit = [&](size_t total, size_t max_line, auto&& line) {
+      const size_t chunk = 1 << 16;
+      for (size_t base = 0; base < total; base += chunk * nthr) {
+        std::vector<std::string> out(nthr);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; ++t)
+          th.emplace_back([&, t] {
+            const size_t lo = base + t * chunk, hi = std::min(total, lo + chunk);
+            if (lo >= hi)
+              return;
+            std::string& s = out[t];
+            s.resize((hi - lo) * max_line);
+            size_t pos = 0;
+            for (size_t i = lo; i < hi; ++i)
+              pos += line(i, &s[pos]);
+            s.resize(pos);
+          });
+        for (auto& x : th)
+          x.join();
+        for (auto& s : out)
+          fwrite(s.data(), 1, s.size(), f);
+      }
+    };
+    const double* V = mesh.vertices.data();
+    const double* C = mesh.colors.data();
+    emit(nv, 96, [&](size_t i, char* dst) {
+      // colour cast to uchar (Q4: un-normalised interpolated colours wrap)
+      return (size_t) sprintf(dst, "%g %g %g %d %d %d\n", V[3 * i], V[3 * i + 1], V[3 * i + 2], (int) (unsigned char) C[3 * i], (int) (unsigned char) C[3 * i + 1], (int) (unsigned char) C[3 * i + 2]);
+    });
+    const int32_t* F = mesh.faces.data();
+    emit(nf, 48, [&](size_t i, char* dst) { return (size_t) sprintf(dst, "3 %d %d %d\n", F[3 * i], F[3 * i + 1], F[3 * i + 2]); });
+    fclose(f);
+    std::cout << "GeoWrapper::extractMesh | written " << nv << " vertices and " << nf << " faces to " << path << std::endl;
   }
 
   int run_marching_cubes(mrh_map* m, int force_generic) {
@@ -78,6 +135,7 @@ namespace {
     }
     if (!m->d_tri_count)
       CK(cudaMalloc(&m->d_tri_count, sizeof(uint32_t)));
+    const double t0 = now_ms();
     CK(cudaMemsetAsync(m->d_tri_count, 0, sizeof(uint32_t), m->stream));
     const uint32_t cap = (uint32_t) std::min<uint64_t>(m->max_num_triangles, 0xFFFFFFFFull);
     k_mc_blocks<<<m->num_sms * 4, 256, 0, m->stream>>>(m->dev, m->live_cur, m->d_tri, m->d_tri_count, cap, force_generic);
@@ -95,8 +153,11 @@ namespace {
     if (n)
       CK(cudaMemcpy(m->mesh.triangles.data() + base, m->d_tri, sizeof(float) * 18 * n, cudaMemcpyDeviceToHost));
     std::cout << "MarchingCubesExtractor::extractIsoSurface | triangles extracted: " << n << std::endl;
+    const double t1 = now_ms();
     if (n)
       merge_triangles(m->mesh, m->mesh.triangles.data() + base, n, (double) m->p.vertices_merging_threshold);
+    m->mesh_ms_kernel += t1 - t0;
+    m->mesh_ms_merge += now_ms() - t1;
     return 0;
   }
 
@@ -115,6 +176,8 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
     return 0;
   }
   m->mesh.clear();
+  m->mesh_ms_stream = m->mesh_ms_kernel = m->mesh_ms_merge = m->mesh_ms_ply = 0;
+  const double t_begin = now_ms();
   std::cout << "GeoWrapper::extractMesh | extracting..." << std::endl;
   HostStore& st     = m->store;
   const float size  = m->p.virtual_voxel_size;
@@ -142,20 +205,30 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
           const float centre[3] = {(float) x * ext, (float) y * ext, (float) z * ext};
           std::vector<GatherRecord> in_recs;
           std::vector<uint32_t> in_vox;
-          HostStore keep;
+          std::vector<uint8_t> inside(st.recs.size());
+          size_t n_in = 0;
           for (size_t i = 0; i < st.recs.size(); ++i) {
             int c[3];
             block_chunk(st.recs[i], size, ext, c);
             const float d[3] = {(float) c[0] * ext - centre[0], (float) c[1] * ext - centre[1], (float) c[2] * ext - centre[2]};
             const float l    = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            const bool in    = l <= std::fabs(radius - chunk_radius);
-            std::vector<GatherRecord>& rr = in ? in_recs : keep.recs;
-            std::vector<uint32_t>& vv     = in ? in_vox : keep.voxels;
-            rr.push_back(st.recs[i]);
-            vv.insert(vv.end(), st.voxels.begin() + i * 3 * kBlockVoxels, st.voxels.begin() + (i + 1) * 3 * kBlockVoxels);
+            inside[i]        = l <= std::fabs(radius - chunk_radius);
+            n_in += inside[i];
           }
-          st.recs.swap(keep.recs);
-          st.voxels.swap(keep.voxels);
+          if (n_in == st.recs.size()) {
+            in_recs.swap(st.recs); // the usual case: one region covers the whole map
+            in_vox.swap(st.voxels);
+          } else if (n_in) {
+            HostStore keep;
+            for (size_t i = 0; i < st.recs.size(); ++i) {
+              std::vector<GatherRecord>& rr = inside[i] ? in_recs : keep.recs;
+              std::vector<uint32_t>& vv     = inside[i] ? in_vox : keep.voxels;
+              rr.push_back(st.recs[i]);
+              vv.insert(vv.end(), st.voxels.begin() + i * 3 * kBlockVoxels, st.voxels.begin() + (i + 1) * 3 * kBlockVoxels);
+            }
+            st.recs.swap(keep.recs);
+            st.voxels.swap(keep.voxels);
+          }
           if (insert_from_host(m, in_recs.data(), in_vox.data(), in_recs.size()))
             return 1;
           if (run_marching_cubes(m, force_generic))
@@ -165,28 +238,11 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
         }
   }
   const size_t nv = m->mesh.vertices.size() / 3, nf = m->mesh.faces.size() / 3;
-  if (path) {
-    // geowrapper.cpp:187-229: ASCII PLY, default ostream precision, colour cast to uchar (Q4)
-    std::ofstream ply(path);
-    if (!ply.is_open()) {
-      std::cerr << "GeoWrapper::extractMesh | Failed to open file for writing: " << path << std::endl;
-      return 0;
-    }
-    ply << "ply\nformat ascii 1.0\nelement vertex " << nv << "\nproperty float x\nproperty float y\nproperty float z\n";
-    ply << "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face " << nf << "\n";
-    ply << "property list uchar int vertex_indices\nend_header\n";
-    const double* V = m->mesh.vertices.data();
-    const double* C = m->mesh.colors.data();
-    for (size_t i = 0; i < nv; ++i) {
-      const unsigned char col[3] = {(unsigned char) C[3 * i], (unsigned char) C[3 * i + 1], (unsigned char) C[3 * i + 2]};
-      ply << V[3 * i] << " " << V[3 * i + 1] << " " << V[3 * i + 2] << " " << (int) col[0] << " " << (int) col[1] << " " << (int) col[2] << "\n";
-    }
-    const int32_t* F = m->mesh.faces.data();
-    for (size_t i = 0; i < nf; ++i)
-      ply << "3 " << F[3 * i] << " " << F[3 * i + 1] << " " << F[3 * i + 2] << "\n";
-    ply.close();
-    std::cout << "GeoWrapper::extractMesh | written " << nv << " vertices and " << nf << " faces to " << path << std::endl;
-  }
+  m->mesh_ms_stream = (now_ms() - t_begin) - m->mesh_ms_kernel - m->mesh_ms_merge;
+  const double t_ply = now_ms();
+  if (path)
+    write_mesh_ply(path, m->mesh);
+  m->mesh_ms_ply = now_ms() - t_ply;
   return 0;
 }
 

@@ -33,12 +33,22 @@ def build_state(n_frames, with_ref=True, width=640, height=480):
     return ours, ref, params
 
 
-def test_marching_cubes_matches_reference():
+def test_marching_cubes_matches_reference(tmp_path):
     ours, ref, _ = build_state(8)
     state = ours.dumpState()
     if ref is not None:
         assert compare_dumps(state, ref.dump())["ok"]
-    ours.extractMesh(None)
+    ply = str(tmp_path / "mesh.ply")
+    ours.extractMesh(ply)
+    # ASCII PLY as geowrapper.cpp:194-229 writes it: default ostream precision (= %g), uchar colours
+    lines = open(ply).read().split("\n")
+    assert lines[:4] == ["ply", "format ascii 1.0", f"element vertex {len(ours.getVertices())}", "property float x"]
+    hdr_end = lines.index("end_header")
+    v0 = lines[hdr_end + 1].split()
+    assert len(v0) == 6 and v0[0] == "%g" % ours.getVertices()[0, 0]
+    f0 = lines[hdr_end + 1 + len(ours.getVertices())].split()
+    assert f0[0] == "3" and [int(x) for x in f0[1:]] == ours.getFaces()[0].tolist()
+    assert len(lines) == hdr_end + 1 + len(ours.getVertices()) + len(ours.getFaces()) + 1
     mine = ours.getTriangles()
     assert len(mine) > 10000
     # every block left the device (streamAllOut inside extractMesh) and sits in the host store
