@@ -115,6 +115,12 @@ int mrh_synchronize(mrh_map* m);
 
 /* GeoWrapper::streamAllOut (geowrapper.cpp:559-561) */
 int mrh_stream_all_out(mrh_map* m);
+/* Multi-GPU meshing support. mrh_store_append adds blocks (records in mrh_dump_entry layout + 512
+ * reference Voxel structs each, as mrh_dump_state returns them - e.g. another shard's dump) to this
+ * handle's host store; mrh_set_shard changes the hash-bucket range the handle accepts (world <= 1 =
+ * everything), so that one rank can stream the gathered shards in and mesh the whole map. */
+int mrh_store_append(mrh_map* m, const mrh_dump_entry* entries, const void* voxels, size_t n);
+int mrh_set_shard(mrh_map* m, int shard_rank, int shard_world);
 /* number of blocks currently held by the host store (the reference's Streamer::grid_) */
 int mrh_store_size(mrh_map* m, size_t* n_blocks);
 /* GeoWrapper::extractMesh (geowrapper.cpp:150-230): marching cubes + host weld + ASCII PLY (path may be NULL: no file) */

@@ -89,6 +89,8 @@ SIGNATURES = {
     "mrh_compute": ([_vp], _i),
     "mrh_synchronize": ([_vp], _i),
     "mrh_stream_all_out": ([_vp], _i),
+    "mrh_store_append": ([_vp, _vp, _vp, C.c_size_t], _i),
+    "mrh_set_shard": ([_vp, _i, _i], _i),
     "mrh_store_size": ([_vp, _P(C.c_size_t)], _i),
     "mrh_extract_mesh": ([_vp, C.c_char_p], _i),
     "mrh_extract_mesh_ex": ([_vp, C.c_char_p, _i], _i),

@@ -544,6 +544,17 @@ int mrh_set_field(mrh_map* m, const char* name, double v) {
   return 0;
 }
 
+int mrh_set_shard(mrh_map* m, int shard_rank, int shard_world) {
+  if (!m)
+    return fail("null handle");
+  if (shard_world > 1 && (shard_rank < 0 || shard_rank >= shard_world))
+    return fail("mrh_set_shard: rank %d outside world %d", shard_rank, shard_world);
+  m->p.shard_rank  = shard_rank;
+  m->p.shard_world = shard_world;
+  refresh_map_params(m);
+  return 0;
+}
+
 int mrh_get_stats(mrh_map* m, mrh_stats* out) {
   GUARD(m);
   if (!out)

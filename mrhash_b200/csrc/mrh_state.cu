@@ -261,6 +261,19 @@ int mrh_stream_all_out(mrh_map* m) {
   return 0;
 }
 
+int mrh_store_append(mrh_map* m, const mrh_dump_entry* entries, const void* voxels, size_t n) {
+  if (!m || (n && (!entries || !voxels)))
+    return fail("null argument");
+  HostStore& st     = m->store;
+  const size_t base = st.recs.size();
+  st.recs.resize(base + n);
+  st.voxels.resize((base + n) * 3 * kBlockVoxels);
+  for (size_t i = 0; i < n; ++i)
+    st.recs[base + i] = {entries[i].x, entries[i].y, entries[i].z, entries[i].resolution, entries[i].ptr};
+  memcpy(st.voxels.data() + base * 3 * kBlockVoxels, voxels, n * 12 * kBlockVoxels);
+  return 0;
+}
+
 int mrh_store_size(mrh_map* m, size_t* n) {
   if (!m || !n)
     return fail("null argument");

@@ -356,6 +356,16 @@ class GeoWrapper:
         check(self._lib.mrh_store_size(self._h, C.byref(n)))
         return n.value
 
+    def storeAppend(self, entries, voxels):
+        """Add blocks (as dumpState returns them, e.g. another shard's) to the host store."""
+        e = np.ascontiguousarray(entries, np.int32)
+        v = np.ascontiguousarray(voxels)
+        assert e.ndim == 2 and e.shape[1] == 5 and v.shape == (len(e), 512) and v.dtype == VOXEL_DTYPE
+        check(self._lib.mrh_store_append(self._h, e.ctypes.data, v.ctypes.data, len(e)))
+
+    def setShard(self, shard_rank, shard_world):
+        check(self._lib.mrh_set_shard(self._h, int(shard_rank), int(shard_world)))
+
     def dumpState(self):
         """(entries [n,5] int32 = x,y,z,resolution,ptr sorted by key; voxels structured [n,512])."""
         n = C.c_size_t()

@@ -83,3 +83,33 @@ def gather_blocks(entries, voxels, dst=0, group=None, device="cpu"):
     vv = np.concatenate([vs[r][: counts[r]].cpu().numpy() for r in range(world)]).view(voxels.dtype).reshape(-1, 512)
     order = np.lexsort((ee[:, 2], ee[:, 1], ee[:, 0]))
     return ee[order], vv[order]
+
+
+def extract_mesh_sharded(geo, path, dst=0, group=None, device="cpu"):
+    """extractMesh for a hash-sharded map: every rank hands its blocks to `dst` (one gather over the
+    process group), which streams all of them into its own handle and meshes the whole map, so
+    neighbour look-ups never cross a shard boundary. Returns True on `dst`. The shards stay as they
+    were on the other ranks; on `dst` the whole map ends up in the host store (as extractMesh leaves it)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        geo.extractMesh(path)
+        return True
+    entries, voxels = geo.dumpState()
+    if rank == dst:
+        geo.streamAllOut()  # own blocks -> host store
+        mine = len(entries)
+    all_e, all_v = gather_blocks(entries, voxels, dst=dst, group=group, device=device)
+    if rank != dst:
+        return False
+    own = owner_of(all_e[:, :3], world, int(geo.getHashNumBuckets())) == rank
+    assert int(own.sum()) == mine
+    geo.storeAppend(all_e[~own], all_v[~own])
+    geo.setShard(0, 1)
+    try:
+        geo.extractMesh(path)
+    finally:
+        geo.setShard(rank, world)
+    return True
