@@ -51,49 +51,62 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed regions (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled during the timed regions (B200_PROFILING.md), through
+    NVML in a background thread (nvidia-smi polling takes driver locks that stall concurrent CUDA API
+    calls: at 100 ms it more than doubled the per-frame wall time of the call-heavy reference arm)."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.02):
         self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+        self.period = period_s
+        self.rows = []  # (time, sm_mhz, sm_max_mhz, [reasons])
+        self._stop = threading.Event()
+        self._thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
-                stdout=subprocess.PIPE,
-                stderr=subprocess.DEVNULL,
-                text=True,
-            )
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.idx]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(get_reasons(h))
+                        self.rows.append((time.time(), sm, mx, [n for n, bit in names.items() if mask & bit]))
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._thread = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
 
     def summary(self, windows):
         sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, r in self.rows:
-            if len(r) < 8 or not any(a <= ts <= b for a, b in windows):
+        for ts, s, m, rs in self.rows:
+            if not any(a - self.period <= ts <= b + self.period for a, b in windows):
                 continue
-            try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            sm.append(s)
+            mx = max(mx, m)
+            reasons.update(rs)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
