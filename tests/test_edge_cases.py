@@ -1,0 +1,176 @@
+"""GPU: edge cases of the compute() path through the C ABI - empty / invalid frames, argument
+errors with the reference's messages, pool exhaustion, full-size streams checked against the
+reference kernels, and store round trips."""
+import numpy as np
+import pytest
+
+from compare import compare_dumps
+from oracle_lib import Oracle, RefCuda, ref_available
+from test_parity_rgbd import NUM_BLOCKS, NUM_BUCKETS, feed, make_all
+
+from mrhash_b200 import GeoWrapper, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def small_map(width=160, height=120, **kw):
+    p = dict(synth.REPLICA_PARAMS)
+    args = dict(num_sdf_blocks=20000, hash_num_buckets=10000, max_num_triangles=100000)
+    args.update(kw)
+    g = GeoWrapper(**p, **args)
+    fx, fy, cx, cy = synth.intrinsics(width, height)
+    g.setCamera(fx, fy, cx, cy, height, width, p["min_depth"], p["max_depth"], 0)
+    return g, p
+
+
+def test_empty_and_invalid_depth_allocate_nothing():
+    g, p = small_map()
+    rgb = np.zeros((120, 160, 3), np.uint8)
+    for depth in (np.zeros((120, 160), np.float32), np.full((120, 160), 1e9, np.float32), np.full((120, 160), -1.0, np.float32), np.full((120, 160), np.nan, np.float32)):
+        g.setCurrPose(np.zeros(3), np.array([0, 0, 0, 1.0]))
+        g.setDepthImage(depth)
+        g.setRGBImage(rgb)
+        g.compute()
+    st = g.getStats()
+    assert st["live_blocks"] == 0 and st["voxels_updated"] == 0 and st["rays_valid"] == 0 and st["heap_free"] == 20000
+    e, v = g.dumpState()
+    assert len(e) == 0
+    g.extractMesh(None)
+    assert len(g.getTriangles()) == 0 and len(g.getVertices()) == 0
+
+
+def test_partially_valid_depth_matches_oracle():
+    """Ragged input: half of the image invalid (0 / beyond max_depth / NaN)."""
+    params = dict(synth.REPLICA_PARAMS)
+    ours, orc, ref = make_all(params, width=160, height=120, num_blocks=20000, num_buckets=10000)
+    t, q, depth, rgb = synth.rgbd_frame(3, n_frames=100, width=160, height=120)
+    depth = depth.copy()
+    depth[:40] = 0.0
+    depth[40:60, :50] = 1e6
+    depth[60:70, 100:] = np.nan
+    feed(ours, [orc, ref], t, q, depth, rgb)
+    rep = compare_dumps(ours.dumpState(), orc.dump())
+    assert rep["ok"] and rep["n_a"] > 100, rep
+    if ref is not None:
+        assert compare_dumps(ours.dumpState(), ref.dump())["ok"]
+
+
+def test_argument_errors_use_the_reference_messages():
+    g, _ = small_map()
+    with pytest.raises(RuntimeError, match=r"GeoWrapper::setDepthImage\|input should be a 2D numpy array"):
+        g.setDepthImage(np.zeros((4, 4, 1), np.float32))
+    with pytest.raises(RuntimeError, match=r"GeoWrapper::setRGBImage\|input should be a 3D numpy array"):
+        g.setRGBImage(np.zeros((4, 4), np.uint8))
+    with pytest.raises(RuntimeError, match=r"GeoWrapper::setRGBImage\|input should have 3 channels"):
+        g.setRGBImage(np.zeros((4, 4, 4), np.uint8))
+    with pytest.raises(RuntimeError, match=r"GeoWrapper::setPointCloud\|input should be a 2D numpy array"):
+        g.setPointCloud(np.zeros(9, np.float32), False)
+    with pytest.raises(RuntimeError, match="same number of points"):
+        g.setPointCloud(np.zeros((5, 3), np.float32), np.zeros((4, 3), np.float32))
+    # frame that does not match the camera
+    g.setDepthImage(np.ones((60, 80), np.float32))
+    g.setRGBImage(np.zeros((60, 80, 3), np.uint8))
+    with pytest.raises(RuntimeError, match="do not match the camera"):
+        g.compute()
+    with pytest.raises(RuntimeError):
+        g.serializeGrid("/tmp/x.bin")
+
+
+def test_float_rgb_is_cast_like_the_binding():
+    """apps/utils/depth_reader.py hands float32 colour; nanobind casts element-wise to uint8."""
+    a, _ = small_map()
+    b, _ = small_map()
+    t, q, depth, rgb = synth.rgbd_frame(1, n_frames=100, width=160, height=120)
+    for g, c in ((a, rgb), (b, rgb.astype(np.float32))):
+        g.setCurrPose(t, q)
+        g.setDepthImage(depth)
+        g.setRGBImage(c)
+        g.compute()
+    (ea, va), (eb, vb) = a.dumpState(), b.dumpState()
+    assert np.array_equal(ea[:, :4], eb[:, :4]) and va.tobytes() == vb.tobytes()
+
+
+def test_pool_exhaustion_is_counted_not_fatal():
+    """allocBlock with an empty heap prints 'mem size exceed' and skips the block
+    (voxel_data_structures.cu:566-569); here it is counted in dropped_heap."""
+    g, _ = small_map(num_sdf_blocks=300, hash_num_buckets=300)
+    for k in range(3):
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=100, width=160, height=120)
+        g.setCurrPose(t, q)
+        g.setDepthImage(depth)
+        g.setRGBImage(rgb)
+        g.compute()
+    st = g.getStats()
+    e, _ = g.dumpState()
+    assert st["dropped_heap"] > 0 and st["heap_free"] >= 0
+    assert len(e) == st["live_blocks"] <= 300 and len(e) + st["heap_free"] == 300
+    assert len({tuple(x[:3]) for x in e}) == len(e)
+
+
+def test_stream_out_and_back_is_lossless():
+    g, _ = small_map()
+    for k in range(4):
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=400, width=160, height=120)
+        g.setCurrPose(t, q)
+        g.setDepthImage(depth)
+        g.setRGBImage(rgb)
+        g.compute()
+    before = g.dumpState()
+    g.streamAllOut()
+    assert g.getStats()["live_blocks"] == 0 and g.getStats()["heap_free"] == 20000
+    g.streamAllOut()  # idempotent
+    assert g.storeSize() == len(before[0])
+    g.extractMesh(None)  # streams everything in, meshes, streams out again
+    assert g.storeSize() == len(before[0])
+    # integrating again after the map left the device starts from an empty hash (reference behaviour)
+    t, q, depth, rgb = synth.rgbd_frame(0, n_frames=400, width=160, height=120)
+    g.setCurrPose(t, q)
+    g.setDepthImage(depth)
+    g.setRGBImage(rgb)
+    g.compute()
+    assert 0 < g.getStats()["live_blocks"] < len(before[0])
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_full_orbit_640x480_matches_reference_kernels():
+    """BASELINE configs[1] at full size: 1000 frames, one full orbit, GC and starve frames on.
+    Block set, heap counter and every voxel field must equal the reference's, except the voxels the
+    starve tie-break (Q11) may pick differently: weights may differ by the starve decrement only."""
+    params = dict(synth.REPLICA_PARAMS)
+    ours, _, _ = make_all(params, with_ref=False, num_blocks=200000, num_buckets=100000)
+    fx, fy, cx, cy = synth.intrinsics(640, 480)
+    ref = RefCuda(params, 200000, 100000)
+    ref.set_camera(fx, fy, cx, cy, 480, 640, params["min_depth"], params["max_depth"], 0)
+    import torch
+
+    for k in range(1000):
+        t, q, R = synth.orbit_pose(k, 1000)
+        d, c = synth.render_rgbd_torch(R, t, 640, 480, device="cuda")
+        depth, rgb = d.cpu().numpy(), c.cpu().numpy()
+        ours.setCurrPose(t, q)
+        ours.setDepthImage(depth)
+        ours.setRGBImage(rgb)
+        ours.compute()
+        ref.compute_rgbd(ours.getCurrPose(), depth, rgb)
+    mine, theirs = ours.dumpState(), ref.dump()
+    st = ours.getStats()
+    rep = compare_dumps(mine, theirs)
+    print("[full orbit]", rep, st)
+    assert st["dropped_heap"] == 0 and st["dropped_table"] == 0
+    assert rep["only_a"] == 0 and rep["only_b"] == 0 and rep["n_a"] > 40000
+    assert rep["sdf_mismatch"] == 0 and rep["sum_squared_mismatch"] == 0
+    assert rep["weight_mismatch"] <= 1e-4 * rep["voxels_compared"] and rep["rgb_mismatch"] <= 1e-4 * rep["voxels_compared"]
+    assert st["heap_free"] == ref.heap_high_free()
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_1280x960_frames_match_reference_kernels():
+    """BASELINE configs[3] frame size."""
+    params = dict(synth.REPLICA_PARAMS)
+    ours, _, ref = make_all(params, width=1280, height=960, with_ref=True)
+    orc = None
+    for k in range(4):
+        t, q, depth, rgb = synth.rgbd_frame(k * 10, n_frames=2000, width=1280, height=960)
+        feed(ours, [orc, ref], t, q, depth, rgb)
+    rep = compare_dumps(ours.dumpState(), ref.dump())
+    assert rep["ok"] and rep["sdf_bitexact"], rep
