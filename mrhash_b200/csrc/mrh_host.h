@@ -28,68 +28,13 @@ namespace mrh {
     }
   };
 
-  // Open-addressing map from a 3 x u32 key to an int (first-seen index), used by the host mesh
-  // merge: vertex positions (float bit patterns, or quantised cells) and faces (index triples).
-  // Replaces std::unordered_map<Vector3d, int> / std::set<tuple> of mesh_extractor.cpp:156-259.
-  struct Key3Map {
-    struct Cell {
-      uint32_t a, b, c;
-      int32_t value; // -1 = empty
-    };
-    std::vector<Cell> cells;
-    size_t count = 0;
-    void clear() {
-      cells.clear();
-      cells.shrink_to_fit();
-      count = 0;
-    }
-    static size_t mix(uint32_t a, uint32_t b, uint32_t c) {
-      uint64_t h = (uint64_t) a * 0x9E3779B97F4A7C15ull;
-      h ^= (uint64_t) b * 0xC2B2AE3D27D4EB4Full + (h >> 29);
-      h ^= (uint64_t) c * 0x165667B19E3779F9ull + (h << 7);
-      h ^= h >> 32;
-      return (size_t) h;
-    }
-    void reserve(size_t n) {
-      size_t cap = 1024;
-      while (cap < 2 * n)
-        cap <<= 1;
-      if (cap <= cells.size())
-        return;
-      std::vector<Cell> old;
-      old.swap(cells);
-      cells.assign(cap, Cell{0, 0, 0, -1});
-      for (const Cell& e : old)
-        if (e.value >= 0)
-          *slot(e.a, e.b, e.c) = e;
-    }
-    Cell* slot(uint32_t a, uint32_t b, uint32_t c) {
-      const size_t mask = cells.size() - 1;
-      size_t i          = mix(a, b, c) & mask;
-      while (cells[i].value >= 0 && !(cells[i].a == a && cells[i].b == b && cells[i].c == c))
-        i = (i + 1) & mask;
-      return &cells[i];
-    }
-    // returns the stored value, inserting `value_if_new` first when the key is absent
-    int32_t find_or_insert(uint32_t a, uint32_t b, uint32_t c, int32_t value_if_new, bool& inserted) {
-      Cell* e  = slot(a, b, c);
-      inserted = e->value < 0;
-      if (inserted) {
-        *e = {a, b, c, value_if_new};
-        ++count;
-      }
-      return e->value;
-    }
-  };
   struct HostMesh {
-    std::vector<float> triangles; // raw soup of the last extraction, 18 floats per triangle
+    std::vector<float> triangles; // host copy of the raw soup (18 floats per triangle), fetched on demand
     std::vector<double> vertices; // V x 3
     std::vector<int32_t> faces;   // F x 3
     std::vector<double> colors;   // V x 3
-    Key3Map vertex_map, face_map;
     void clear() {
       triangles.clear(), vertices.clear(), faces.clear(), colors.clear();
-      vertex_map.clear(), face_map.clear();
     }
   };
 
@@ -160,9 +105,12 @@ struct mrh_map {
   float* d_tri           = nullptr;
   size_t d_tri_cap       = 0;
   uint32_t* d_tri_count  = nullptr;
+  size_t soup_in_tri     = 0;       // triangles of the last marching-cubes run, still in d_tri
+  float* d_soup_acc      = nullptr; // soups of earlier regions of the same extraction
+  size_t soup_acc_n = 0, soup_acc_cap = 0;
   mrh::HostStore store;
   mrh::HostMesh mesh;
-  // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel + D2H, host merge, PLY
+  // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel, device weld + D2H of the mesh, PLY
   double mesh_ms_stream = 0, mesh_ms_kernel = 0, mesh_ms_merge = 0, mesh_ms_ply = 0;
 };
 
@@ -171,6 +119,7 @@ namespace mrh {
   int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels);
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
   int carve_low_blocks(mrh_map* m, uint32_t n_low);
+  int weld_on_device(mrh_map* m, const float* d_soup, size_t n_tri, double eps);
   int integrate_rgbd(mrh_map* m);
   int integrate_points(mrh_map* m);
   FrameDev make_frame(const mrh_map* m);

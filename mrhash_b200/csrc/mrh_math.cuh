@@ -130,9 +130,11 @@ __device__ __forceinline__ float get_depth(const CameraDev& c, f3 p) {
     return p.z;
   return __fsqrt_rn(ffma(p.z, p.z, ffma(p.x, p.x, fmul(p.y, p.y))));
 }
-// the depth the reference reads back from its float3 cloud image (camera.cu:5-19 then getDepth)
+// the depth the reference reads back from its float3 cloud image (camera.cu:5-19 then getDepth).
+// A NaN depth passes both comparisons, exactly as in calculateCloudKernel: such a pixel allocates
+// nothing (fminf drops the NaN bounds, dmin == dmax) but poisons the voxels that project onto it.
 __device__ __forceinline__ float cloud_depth(const CameraDev& c, uint32_t row, uint32_t col, float raw) {
-  if (raw <= c.min_depth || !(raw <= c.max_depth))
+  if (raw <= c.min_depth || raw > c.max_depth)
     return 0.f;
   if (c.model == 0)
     return raw;

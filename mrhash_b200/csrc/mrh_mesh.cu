@@ -1,6 +1,7 @@
 // mrh_mesh.cu — GeoWrapper::extractMesh (geowrapper.cpp:150-230): region loop over the host store,
-// marching cubes on the device, host merge of the triangle soup (MeshExtractor::processTriangles,
-// mesh_extractor.cpp:9-76,156-259), ASCII PLY.
+// marching cubes on the device, weld of the triangle soup on the device (mrh_weld.cu, replacing the
+// host post-process MeshExtractor::processTriangles, mesh_extractor.cpp:9-76,156-259), ASCII PLY.
+// The soup never leaves the device unless a caller asks for it (mrh_get_triangles).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -11,6 +12,7 @@
 #include <string>
 #include <thread>
 
+#include "mrh_fmt.h"
 #include "mrh_host.h"
 #include "mrh_mesh.cuh"
 
@@ -36,45 +38,6 @@ namespace {
       const float p  = pw / ext;
       const float s  = (float) ((0.f < p) - (p < 0.f));
       out[k]         = (int) (p + s * 0.5f);
-    }
-  }
-
-  // MeshExtractor::processTriangles with merge_mesh_ = true, incrementally: vertices already in the
-  // mesh keep their first-seen index, exactly as re-running removeDuplicateVerticesTriangle over
-  // (unique old, new) does.
-  void merge_triangles(HostMesh& mesh, const float* tris, size_t n, double eps) {
-    const double inv_eps = eps != 0.0 ? 1.0 / eps : 0.0;
-    mesh.vertex_map.reserve(mesh.vertex_map.count + 3 * n);
-    mesh.face_map.reserve(mesh.face_map.count + n);
-    mesh.vertices.reserve(mesh.vertices.size() + 6 * n);
-    mesh.colors.reserve(mesh.colors.size() + 6 * n);
-    mesh.faces.reserve(mesh.faces.size() + 3 * n);
-    for (size_t t = 0; t < n; ++t) {
-      int32_t idx[3];
-      for (int j = 0; j < 3; ++j) {
-        const float* v = tris + t * 18 + j * 6;
-        uint32_t key[3];
-        if (eps == 0.0) {
-          // exact merge: byte-wise equality of the doubles == of the floats they were widened from
-          memcpy(key, v, 12);
-        } else {
-          for (int k = 0; k < 3; ++k)
-            key[k] = (uint32_t) (int) std::floor((double) v[k] * inv_eps);
-        }
-        bool inserted;
-        idx[j] = mesh.vertex_map.find_or_insert(key[0], key[1], key[2], (int32_t) (mesh.vertices.size() / 3), inserted);
-        if (inserted) {
-          mesh.vertices.insert(mesh.vertices.end(), {(double) v[0], (double) v[1], (double) v[2]});
-          mesh.colors.insert(mesh.colors.end(), {(double) v[3], (double) v[4], (double) v[5]});
-        }
-      }
-      if (idx[0] == idx[1] || idx[0] == idx[2] || idx[1] == idx[2])
-        continue; // degenerate after the merge
-      bool inserted;
-      mesh.face_map.find_or_insert((uint32_t) idx[0], (uint32_t) idx[1], (uint32_t) idx[2], 0, inserted);
-      if (!inserted)
-        continue; // duplicate face
-      mesh.faces.insert(mesh.faces.end(), {idx[0], idx[1], idx[2]});
     }
   }
 
@@ -118,16 +81,59 @@ namespace {
     const double* C = mesh.colors.data();
     emit(nv, 96, [&](size_t i, char* dst) {
       // colour cast to uchar (Q4: un-normalised interpolated colours wrap)
-      return (size_t) sprintf(dst, "%g %g %g %d %d %d\n", V[3 * i], V[3 * i + 1], V[3 * i + 2], (int) (unsigned char) C[3 * i], (int) (unsigned char) C[3 * i + 1], (int) (unsigned char) C[3 * i + 2]);
+      char* p = dst;
+      for (int k = 0; k < 3; ++k) {
+        p += fmt_g6(V[3 * i + k], p);
+        *p++ = ' ';
+      }
+      for (int k = 0; k < 3; ++k) {
+        p += fmt_uint((uint32_t) (unsigned char) C[3 * i + k], p);
+        *p++ = k == 2 ? '\n' : ' ';
+      }
+      return (size_t) (p - dst);
     });
     const int32_t* F = mesh.faces.data();
-    emit(nf, 48, [&](size_t i, char* dst) { return (size_t) sprintf(dst, "3 %d %d %d\n", F[3 * i], F[3 * i + 1], F[3 * i + 2]); });
+    emit(nf, 48, [&](size_t i, char* dst) {
+      char* p = dst;
+      *p++ = '3';
+      for (int k = 0; k < 3; ++k) {
+        *p++ = ' ';
+        p += fmt_int(F[3 * i + k], p);
+      }
+      *p++ = '\n';
+      return (size_t) (p - dst);
+    });
     fclose(f);
     std::cout << "GeoWrapper::extractMesh | written " << nv << " vertices and " << nf << " faces to " << path << std::endl;
   }
 
+  // soup of the regions meshed so far moves to the accumulation buffer (only a map larger than one
+  // streaming region, radius 10 x max_depth, ever takes this path)
+  int stash_soup(mrh_map* m) {
+    if (m->soup_in_tri == 0)
+      return 0;
+    const size_t need = m->soup_acc_n + m->soup_in_tri;
+    if (need > m->soup_acc_cap) {
+      const size_t cap = std::max(need, 2 * m->soup_acc_cap);
+      float* grown     = nullptr;
+      CK(cudaMalloc(&grown, sizeof(float) * 18 * cap));
+      if (m->soup_acc_n)
+        CK(cudaMemcpyAsync(grown, m->d_soup_acc, sizeof(float) * 18 * m->soup_acc_n, cudaMemcpyDeviceToDevice, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+      cudaFree(m->d_soup_acc);
+      m->d_soup_acc = grown, m->soup_acc_cap = cap;
+    }
+    CK(cudaMemcpyAsync(m->d_soup_acc + 18 * m->soup_acc_n, m->d_tri, sizeof(float) * 18 * m->soup_in_tri, cudaMemcpyDeviceToDevice, m->stream));
+    m->soup_acc_n += m->soup_in_tri;
+    m->soup_in_tri = 0;
+    return 0;
+  }
+
   int run_marching_cubes(mrh_map* m, int force_generic) {
+    if (stash_soup(m))
+      return 1;
     if (m->max_num_triangles > m->d_tri_cap) {
+      CK(cudaStreamSynchronize(m->stream));
       cudaFree(m->d_tri);
       m->d_tri = nullptr;
       CK(cudaMalloc(&m->d_tri, sizeof(float) * 18 * m->max_num_triangles));
@@ -148,17 +154,20 @@ namespace {
       fprintf(stderr, "appendTriangle | exceeded max triangles: %u >= %u\n", n, cap);
       n = cap;
     }
-    const size_t base = m->mesh.triangles.size();
-    m->mesh.triangles.resize(base + (size_t) n * 18);
-    if (n)
-      CK(cudaMemcpy(m->mesh.triangles.data() + base, m->d_tri, sizeof(float) * 18 * n, cudaMemcpyDeviceToHost));
+    m->soup_in_tri = n;
     std::cout << "MarchingCubesExtractor::extractIsoSurface | triangles extracted: " << n << std::endl;
-    const double t1 = now_ms();
-    if (n)
-      merge_triangles(m->mesh, m->mesh.triangles.data() + base, n, (double) m->p.vertices_merging_threshold);
-    m->mesh_ms_kernel += t1 - t0;
-    m->mesh_ms_merge += now_ms() - t1;
+    m->mesh_ms_kernel += now_ms() - t0;
     return 0;
+  }
+
+  // the soup of the last extraction: [d_soup, d_soup + 18 * n)
+  const float* device_soup(const mrh_map* m, size_t& n) {
+    if (m->soup_acc_n) {
+      n = m->soup_acc_n;
+      return m->d_soup_acc;
+    }
+    n = m->soup_in_tri;
+    return m->d_tri;
   }
 
 } // namespace
@@ -176,6 +185,7 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
     return 0;
   }
   m->mesh.clear();
+  m->soup_in_tri = m->soup_acc_n = 0;
   m->mesh_ms_stream = m->mesh_ms_kernel = m->mesh_ms_merge = m->mesh_ms_ply = 0;
   const double t_begin = now_ms();
   std::cout << "GeoWrapper::extractMesh | extracting..." << std::endl;
@@ -237,7 +247,17 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
             return 1;
         }
   }
-  const size_t nv = m->mesh.vertices.size() / 3, nf = m->mesh.faces.size() / 3;
+  {
+    // processTriangles with merge_mesh_ = true over the soups of all regions, in region order
+    const double t_weld = now_ms();
+    if (m->soup_acc_n && stash_soup(m))
+      return 1;
+    size_t n_tri      = 0;
+    const float* soup = device_soup(m, n_tri);
+    if (weld_on_device(m, soup, n_tri, (double) m->p.vertices_merging_threshold))
+      return 1;
+    m->mesh_ms_merge = now_ms() - t_weld;
+  }
   m->mesh_ms_stream = (now_ms() - t_begin) - m->mesh_ms_kernel - m->mesh_ms_merge;
   const double t_ply = now_ms();
   if (path)
@@ -261,8 +281,16 @@ int mrh_get_mesh(mrh_map* m, const double** v, const int32_t** f, const double**
 int mrh_get_triangles(mrh_map* m, const float** t, size_t* n) {
   if (!m || !t || !n)
     return fail("null argument");
+  size_t n_tri      = 0;
+  const float* soup = device_soup(m, n_tri);
+  if (m->mesh.triangles.size() != n_tri * 18) {
+    CK(cudaSetDevice(m->device));
+    m->mesh.triangles.resize(n_tri * 18);
+    if (n_tri)
+      CK(cudaMemcpy(m->mesh.triangles.data(), soup, sizeof(float) * 18 * n_tri, cudaMemcpyDeviceToHost));
+  }
   *t = m->mesh.triangles.data();
-  *n = m->mesh.triangles.size() / 18;
+  *n = n_tri;
   return 0;
 }
 

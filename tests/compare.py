@@ -32,12 +32,19 @@ def compare_dumps(a, b, sdf_rtol=1e-5, sdf_atol=1e-7):
     rgb_bad = ((xa["r"] != xb["r"]) | (xa["g"] != xb["g"]) | (xa["b"] != xb["b"])) & valid
     rep["rgb_mismatch"] = int(rgb_bad.sum())
     for f in ("sdf", "sum_squared"):
-        d = np.abs(xa[f].astype(np.float64) - xb[f].astype(np.float64))
-        tol = sdf_atol + sdf_rtol * np.maximum(np.abs(xa[f]), np.abs(xb[f]))
-        bad = (d > tol) & valid
+        # NaN (a NaN depth pixel poisons the voxels under it, in the reference too) must meet NaN; the
+        # payload bits of a NaN are not part of the contract (GPU: canonical 0x7FFFFFFF, x86: propagated)
+        na, nb = np.isnan(xa[f]), np.isnan(xb[f])
+        both = na & nb
+        with np.errstate(invalid="ignore"):
+            d = np.abs(xa[f].astype(np.float64) - xb[f].astype(np.float64))
+            tol = sdf_atol + sdf_rtol * np.maximum(np.abs(xa[f]), np.abs(xb[f]))
+            bad = ((d > tol) | (na != nb)) & valid
+        d = np.where(both | (na != nb), 0.0, d)
         rep[f + "_mismatch"] = int(bad.sum())
         rep[f + "_max_abs_diff"] = float(d[valid].max()) if valid.any() else 0.0
-        rep[f + "_bitexact"] = bool((xa[f].view(np.uint32) == xb[f].view(np.uint32))[valid].all()) if valid.any() else True
+        rep[f + "_bitexact"] = bool(((xa[f].view(np.uint32) == xb[f].view(np.uint32)) | both)[valid].all() and not bad.any()) if valid.any() else True
+        rep[f + "_nan"] = int((both & valid).sum())
     rep["voxels_compared"] = int(valid.sum())
     rep["ok"] = all(rep[k] == 0 for k in ("only_a", "only_b", "resolution_mismatch", "weight_mismatch", "rgb_mismatch", "sdf_mismatch", "sum_squared_mismatch"))
     return rep

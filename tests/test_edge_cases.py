@@ -52,7 +52,9 @@ def test_partially_valid_depth_matches_oracle():
     rep = compare_dumps(ours.dumpState(), orc.dump())
     assert rep["ok"] and rep["n_a"] > 100, rep
     if ref is not None:
-        assert compare_dumps(ours.dumpState(), ref.dump())["ok"]
+        rep = compare_dumps(ours.dumpState(), ref.dump())
+        # the NaN pixels fuse NaN into the voxels below them, in the reference and here alike
+        assert rep["ok"] and rep["sdf_nan"] > 0, rep
 
 
 def test_argument_errors_use_the_reference_messages():

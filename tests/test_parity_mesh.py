@@ -135,3 +135,47 @@ def test_serialize_data_round_trip(tmp_path):
     # a second streamAllOut + clearBuffers leaves nothing behind
     ours.clearBuffers()
     assert ours.storeSize() == 0
+
+
+def _first_seen_weld(tris, eps):
+    """numpy restatement of MeshExtractor::processTriangles (mesh_extractor.cpp:9-76,156-259):
+    vertices numbered in first-seen order of the soup, degenerate and repeated faces dropped."""
+    P = np.ascontiguousarray(tris[:, :, :3].reshape(-1, 3))
+    Cc = tris[:, :, 3:].reshape(-1, 3)
+    if eps == 0.0:
+        keys = P.view(np.uint32).astype(np.int64)
+    else:
+        keys = np.floor(P.astype(np.float64) * (1.0 / eps)).astype(np.int64)
+    _, first_idx, inverse = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first_idx, kind="stable")
+    rank = np.empty(len(order), np.int64)
+    rank[order] = np.arange(len(order))
+    ids = rank[np.asarray(inverse).ravel()].reshape(-1, 3)
+    V = P[first_idx[order]].astype(np.float64)
+    C = Cc[first_idx[order]].astype(np.float64)
+    F = ids[(ids[:, 0] != ids[:, 1]) & (ids[:, 0] != ids[:, 2]) & (ids[:, 1] != ids[:, 2])]
+    _, ff = np.unique(F, axis=0, return_index=True)
+    return V, F[np.sort(ff)].astype(np.int32), C
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.004])
+def test_device_weld_matches_first_seen_merge(eps):
+    params = dict(synth.REPLICA_PARAMS)
+    params["vertices_merging_threshold"] = eps
+    fx, fy, cx, cy = synth.intrinsics(640, 480)
+    g = GeoWrapper(**params, num_sdf_blocks=NUM_BLOCKS, hash_num_buckets=NUM_BUCKETS, max_num_triangles=MAX_TRIS)
+    g.setCamera(fx, fy, cx, cy, 480, 640, params["min_depth"], params["max_depth"], 0)
+    for k in range(7):
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000)
+        feed(g, [], t, q, depth, rgb)
+    g.extractMesh(None)
+    tris = g.getTriangles()
+    assert len(tris) > 10000
+    V, F, C = _first_seen_weld(tris, eps)
+    gv, gf, gc = g.getVertices(), g.getFaces(), g.getColors()
+    print(f"[weld eps={eps}] triangles {len(tris)} -> vertices {len(gv)} faces {len(gf)} (restatement {len(V)} / {len(F)})")
+    assert gv.shape == V.shape and gf.shape == F.shape
+    assert np.array_equal(gv, V) and np.array_equal(gc, C) and np.array_equal(gf, F)
+    # welding twice gives the same mesh (the device weld is deterministic)
+    g2v = g.getVertices()
+    assert np.array_equal(g2v, gv)
