@@ -96,6 +96,10 @@ int mrh_get_pose_matrix(mrh_map* m, float out[16]);
 /* GeoWrapper::setCameraInLidar (geowrapper.cpp:94-96) */
 int mrh_set_camera_in_lidar(mrh_map* m, const float T[16]);
 
+/* Frame setters. Pageable host memory is copied before the call returns (the reference's setters
+ * copy element-wise, geowrapper.cpp:261-273). Page-locked (cudaHostAlloc / cudaHostRegister) memory
+ * is read by DMA without a staging copy, and that transfer completes inside the next mrh_compute():
+ * such a buffer must not be modified between the setter and the return of mrh_compute(). */
 /* GeoWrapper::setDepthImage (geowrapper.cpp:246-274): host float32 [rows, cols], copied */
 int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols);
 /* GeoWrapper::setRGBImage (geowrapper.cpp:276-298): host uint8 [rows, cols, 3], copied */
@@ -131,6 +135,32 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path_or_null, int force_generic)
 int mrh_get_mesh(mrh_map* m, const double** vertices, const int32_t** faces, const double** colors, size_t* n_vertices, size_t* n_faces);
 /* raw triangle soup of the last extract (72-byte Triangle records, voxel_hash_utils.cuh:46-64) */
 int mrh_get_triangles(mrh_map* m, const float** triangles, size_t* n_triangles);
+/* ---- sharded meshing (no reference counterpart: the reference is single-GPU; marching_cubes.cu:72-214
+ * reads the 26 neighbour blocks, which under the hash-bucket partition live on other ranks).
+ * All pointers named d_* are DEVICE pointers on the handle's device (buffers the caller exchanges
+ * with NCCL). Sequence per rank: mrh_halo_requests -> all-to-all of the keys to their owners ->
+ * mrh_halo_pack on the owner -> all-to-all of the records back -> mrh_halo_insert ->
+ * mrh_mesh_local -> mrh_halo_clear. */
+/* bytes of one exchanged record: 16-byte header (int32 resolution, -1 = key not held) + (sdf, rgbw)
+ * pairs of the block's one-voxel shell (296 voxels; full != 0: all 512, needed with resolution-1 blocks) */
+size_t mrh_halo_record_bytes(int full);
+/* unique keys (x,y,z int32) of the neighbours of owned blocks that another rank owns; *n may exceed
+ * cap, in which case only cap keys were written and the call must be repeated with a larger buffer */
+int mrh_halo_requests(mrh_map* m, int32_t* d_keys_xyz, size_t cap, size_t* n);
+/* owner side: one record per requested key */
+int mrh_halo_pack(mrh_map* m, const int32_t* d_keys_xyz, size_t n, int full, void* d_records);
+/* requester side: received records become ghost blocks (sampled by the mesher, never meshed themselves) */
+int mrh_halo_insert(mrh_map* m, const int32_t* d_keys_xyz, const void* d_records, size_t n, int full);
+/* removes the ghost blocks again; the map is exactly as before mrh_halo_insert */
+int mrh_halo_clear(mrh_map* m);
+/* marching cubes over the owned blocks where they are (no stream-out); the soup stays on the device */
+int mrh_mesh_local(mrh_map* m, size_t* n_triangles);
+/* copies the soup of the last extraction into a device buffer of cap_triangles x 18 floats */
+int mrh_copy_triangles_device(mrh_map* m, float* d_dst, size_t cap_triangles);
+/* MeshExtractor::processTriangles (mesh_extractor.cpp:9-76) + the PLY writer (geowrapper.cpp:194-229) over a
+ * soup in device memory (e.g. the soups of all ranks gathered with NCCL); result via mrh_get_mesh */
+int mrh_weld_device_soup(mrh_map* m, const float* d_soup, size_t n_triangles, const char* path_or_null);
+
 /* GeoWrapper::serializeData (geowrapper.cpp:563-565) */
 int mrh_serialize_data(mrh_map* m, const char* hash_path, const char* voxel_path);
 /* GeoWrapper::clearBuffers (geowrapper.cpp:552-557) */

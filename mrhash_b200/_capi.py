@@ -108,6 +108,14 @@ SIGNATURES = {
     "mrh_get_stream": ([_vp, _P(_vp)], _i),
     "mrh_get_launch_count": ([_vp, _P(C.c_uint64)], _i),
     "mrh_dump_state": ([_vp, _vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),
+    "mrh_halo_record_bytes": ([_i], C.c_size_t),
+    "mrh_halo_requests": ([_vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),
+    "mrh_halo_pack": ([_vp, _vp, C.c_size_t, _i, _vp], _i),
+    "mrh_halo_insert": ([_vp, _vp, _vp, C.c_size_t, _i], _i),
+    "mrh_halo_clear": ([_vp], _i),
+    "mrh_mesh_local": ([_vp, _P(C.c_size_t)], _i),
+    "mrh_copy_triangles_device": ([_vp, _vp, C.c_size_t], _i),
+    "mrh_weld_device_soup": ([_vp, _vp, C.c_size_t, C.c_char_p], _i),
 }
 
 _lib = None

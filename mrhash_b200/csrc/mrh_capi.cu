@@ -121,9 +121,8 @@ static void free_map(mrh_map* m) {
     }
   if (m->copy_stream)
     cudaStreamDestroy(m->copy_stream);
-  cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc);
+  cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
-  cudaFreeHost(m->h_n_updates);
   cudaFreeHost(m->h_ctr);
   for (int i = 0; i < 8; ++i)
     if (m->ev_k[i])
@@ -162,11 +161,16 @@ static void refresh_map_params(mrh_map* m) {
 
 // Ingest (replaces the blocking DualMatrix::toDevice inside compute(), cuda_matrix.cuh:129).
 // The copy goes to the other device image on the copy stream, after the frame that last read that
-// image has finished. Pinned caller memory is copied from directly and the call waits for the
-// transfer (setters copy: the caller may reuse its buffer on return); pageable memory goes through
-// a pinned staging buffer and the call returns once the bytes are staged.
+// image has finished. Pageable caller memory goes through a pinned staging buffer and the call
+// returns once the bytes are staged (setters copy: the caller may reuse its buffer on return).
+// Page-locked caller memory is read by DMA directly; that transfer is only waited for at the end of
+// compute(), so such a buffer must stay unchanged until compute() returns (include/mrhash_b200.h).
 template <typename T, typename F>
 static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n, F fill) {
+  if (in.pending_direct) { // set twice without a compute() in between
+    CK(cudaEventSynchronize(in.copied[in.which]));
+    in.pending_direct = false;
+  }
   const int w        = in.which ^ 1;
   const size_t bytes = sizeof(T) * n;
   if (bytes > in.d_cap[w]) {
@@ -186,7 +190,7 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
   if (direct) {
     CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, m->copy_stream));
     CK(cudaEventRecord(in.copied[w], m->copy_stream));
-    CK(cudaEventSynchronize(in.copied[w]));
+    in.pending_direct = true;
   } else {
     if (bytes > in.h_cap[w]) {
       CK(cudaEventSynchronize(in.copied[w]));
@@ -260,7 +264,6 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
       CK(cudaEventCreateWithFlags(&in->consumed[i], cudaEventDisableTiming));
     }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
-  CK(cudaMallocHost(&m->h_n_updates, sizeof(uint32_t)));
   for (int i = 0; i < 8; ++i)
     CK(cudaEventCreate(&m->ev_k[i]));
   cudaDeviceProp prop;
@@ -457,9 +460,16 @@ int mrh_compute(mrh_map* m) {
   }
   refresh_map_params(m);
   Ingest* used[3] = {rgbd ? &m->in_depth : nullptr, rgbd ? &m->in_rgb : nullptr, m->n_points ? &m->in_points : nullptr};
+  // the ray walk needs the depth image (or the points) only: the colour transfer overlaps it and is
+  // waited for in front of the first fusion kernel (integrate_rgbd)
+  m->rgb_ready = nullptr;
   for (Ingest* in : used)
-    if (in && in->active)
-      CK(cudaStreamWaitEvent(m->stream, in->copied[in->which], 0));
+    if (in && in->active) {
+      if (in == &m->in_rgb)
+        m->rgb_ready = in->copied[in->which];
+      else
+        CK(cudaStreamWaitEvent(m->stream, in->copied[in->which], 0));
+    }
   CK(cudaEventRecord(m->ev0, m->stream));
   if (rgbd && integrate_rgbd(m))
     return 1;
@@ -469,6 +479,12 @@ int mrh_compute(mrh_map* m) {
   for (Ingest* in : used)
     if (in && in->active)
       CK(cudaEventRecord(in->consumed[in->which], m->stream));
+  // transfers that read the caller's page-locked memory directly: the caller owns it again on return
+  for (Ingest* in : used)
+    if (in && in->pending_direct) {
+      CK(cudaEventSynchronize(in->copied[in->which]));
+      in->pending_direct = false;
+    }
   return 0;
 }
 
@@ -513,6 +529,8 @@ int mrh_get_field(mrh_map* m, const char* name, double* out) {
   else if (n == "LastMeshKernelMs") *out = m->mesh_ms_kernel;
   else if (n == "LastMeshMergeMs") *out = m->mesh_ms_merge;
   else if (n == "LastMeshPlyMs") *out = m->mesh_ms_ply;
+  else if (n == "Device") *out = m->device;
+  else if (n == "LowResolutionBlocks") *out = (double) (m->p.sdf_var_threshold > 0.f || m->h_ctr->low_live > 0);
   else
     return fail("mrh_get_field: unknown field '%s'", name);
   return 0;

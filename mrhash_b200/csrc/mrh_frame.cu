@@ -2,8 +2,8 @@
 //
 // VoxelContainer::integrate (voxel_data_structures.cpp:90-134) issues ~12 kernels, ~10 blocking
 // copies and ~15 device synchronisations per frame. Here an RGB-D frame is 3 kernels on one stream
-// (4 more on the every-n-th starve frame) and the host never waits; the point-cloud path waits once
-// per frame for a 4-byte record count (the sort needs it).
+// (4 more on the every-n-th starve frame) and the host never waits, on the point-cloud path either
+// (its sort runs over a record count the host knows in advance).
 #include <algorithm>
 #include <cmath>
 
@@ -159,6 +159,8 @@ int integrate_rgbd(mrh_map* m) {
     k_front<<<tiles_x * tiles_y + n_vis_ctas, 256, 0, s>>>(d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
     CKL();
     mark(1);
+    if (m->rgb_ready)
+      cudaStreamWaitEvent(s, m->rgb_ready, 0);
     mark(2);
     if (fused_gc)
       k_integrate<true><<<m->integrate_grid, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
@@ -178,6 +180,8 @@ int integrate_rgbd(mrh_map* m) {
     mark(1);
     k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 1);
     CKL();
+    if (m->rgb_ready)
+      cudaStreamWaitEvent(s, m->rgb_ready, 0);
     mark(2);
     k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, 0);
     CKL();
@@ -217,38 +221,36 @@ int integrate_rgbd(mrh_map* m) {
   return 0;
 }
 
-// integrate3D (:1381-1401): emit -> sort -> apply
-static int fuse_points(FrameCtx& c, const FrameDev& f) {
+// integrate3D (:1381-1401): emit -> stable sort by voxel address -> apply. K is the key type.
+template <typename K>
+static int fuse_points_typed(FrameCtx& c, const FrameDev& f, int key_bits) {
   mrh_map* m      = c.m;
   const MapDev& d = m->dev;
   cudaStream_t s  = m->stream;
-  const uint32_t n = (uint32_t) m->n_points;
-  const int grid_pts = (int) ((n + 255) / 256);
-  if (cudaMemsetAsync(&d.ctr->n_updates, 0, sizeof(uint32_t), s) != cudaSuccess)
-    return fail("point path: clearing the record count failed");
-  k_points_emit<<<grid_pts, 256, 0, s>>>(d, f, m->d_points, n, m->d_upd_keys[0], m->d_upd_vals[0], (uint32_t) m->upd_cap);
+  const uint32_t n = (uint32_t) m->n_points, slots = m->upd_slots;
+  const size_t items = (size_t) n * slots;
+  K* keys[2]   = {(K*) m->d_upd_keys[0], (K*) m->d_upd_keys[1]};
+  const K hole = (K) ~(K) 0; // what the memset leaves in an unused slot; its low key_bits sort after every address
+  if (cudaMemsetAsync(keys[0], 0xFF, sizeof(K) * items, s) != cudaSuccess)
+    return fail("point path: clearing the record slots failed");
+  k_points_emit<K><<<(int) ((n + 255) / 256), 256, 0, s>>>(d, f, m->d_points, n, keys[0], m->d_upd_vals[0], slots);
   CKL();
-  m->launches += 1;
-  // the sort needs the record count on the host: one 4-byte read-back per pass
-  if (cudaMemcpyAsync(m->h_n_updates, &d.ctr->n_updates, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
-    return fail("point path: reading the record count failed: %s", cudaGetErrorString(cudaGetLastError()));
-  const uint32_t n_upd           = (uint32_t) std::min<size_t>(*m->h_n_updates, m->upd_cap);
-  const unsigned long long* keys = m->d_upd_keys[0];
-  const float* vals              = m->d_upd_vals[0];
-  if (n_upd > 1) {
-    int addr_bits = 1;
-    while ((1ull << addr_bits) < (unsigned long long) d.num_blocks * 512ull)
-      ++addr_bits;
-    size_t tmp = m->sort_tmp_bytes;
-    if (cub::DeviceRadixSort::SortPairs(m->d_sort_tmp, tmp, m->d_upd_keys[0], m->d_upd_keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) n_upd, 0, kPointIdxBits + addr_bits, s) != cudaSuccess)
-      return fail("point path: radix sort failed");
-    keys = m->d_upd_keys[1], vals = m->d_upd_vals[1];
-    m->launches += 4;
-  }
-  k_points_apply<<<c.grid_list, 256, 0, s>>>(d, keys, vals, (uint32_t) m->upd_cap);
+  size_t tmp = m->sort_tmp_bytes;
+  if (cub::DeviceRadixSort::SortPairs(m->d_sort_tmp, tmp, keys[0], keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) items, 0, key_bits, s) != cudaSuccess)
+    return fail("point path: radix sort failed");
+  k_points_apply<K><<<c.grid_list, 256, 0, s>>>(d, keys[1], m->d_upd_vals[1], (uint32_t) items, hole);
   CKL();
-  m->launches += 1;
+  m->launches += 3 + (key_bits + 7) / 8;
   return 0;
+}
+
+static int fuse_points(FrameCtx& c, const FrameDev& f) {
+  // pool address of a voxel (block * 512 + index) plus one more bit for the hole key
+  int key_bits = 1;
+  while ((1ull << key_bits) < (unsigned long long) c.m->dev.num_blocks * 512ull)
+    ++key_bits;
+  ++key_bits;
+  return key_bits <= 32 ? fuse_points_typed<uint32_t>(c, f, key_bits) : fuse_points_typed<unsigned long long>(c, f, key_bits);
 }
 
 int integrate_points(mrh_map* m) {
@@ -258,13 +260,16 @@ int integrate_points(mrh_map* m) {
   const FrameDev& f  = c.f;
   cudaStream_t s     = m->stream;
   const uint32_t n   = (uint32_t) m->n_points;
-  if (m->n_points >= (1ull << kPointIdxBits))
-    return fail("point cloud too large: %zu points (limit %u)", m->n_points, 1u << kPointIdxBits);
-
-  // staging for the (voxel, point, sdf) records: a ray of length 2t crosses at most 3*(2t/size)+4 voxels
-  const float t_max   = m->p.sdf_truncation + m->p.sdf_truncation_scale * m->max_integration_distance;
-  const size_t per_pt = (size_t) std::min(3.0 * std::ceil(2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
-  const size_t want   = std::min<size_t>((size_t) n * per_pt, (size_t) 1 << 28);
+  // record slots: a ray of length 2t crosses at most 3*(2t/size)+4 voxels; every point owns that many
+  // (the sort runs over points x slots items, a count the host knows without asking the device)
+  const float t_max    = m->p.sdf_truncation + m->p.sdf_truncation_scale * m->max_integration_distance;
+  const size_t per_pt  = (size_t) std::min(3.0 * std::ceil(2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
+  const size_t max_items = (size_t) 1 << 28;
+  const size_t slots   = std::max<size_t>(1, std::min(per_pt, max_items / std::max<size_t>(n, 1)));
+  const size_t want    = (size_t) n * slots;
+  if (want > max_items)
+    return fail("point cloud too large: %zu points", m->n_points);
+  m->upd_slots = (uint32_t) slots;
   if (want > m->upd_cap) {
     cudaStreamSynchronize(s);
     for (int i = 0; i < 2; ++i) {
@@ -275,7 +280,7 @@ int integrate_points(mrh_map* m) {
     }
     m->upd_cap = want;
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_upd_keys[0], m->d_upd_keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) want, 0, 64, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned long long*) nullptr, (unsigned long long*) nullptr, (float*) nullptr, (float*) nullptr, (int) want, 0, 64, s);
     cudaFree(m->d_sort_tmp);
     m->d_sort_tmp = nullptr;
     if (cudaMalloc(&m->d_sort_tmp, tmp) != cudaSuccess)

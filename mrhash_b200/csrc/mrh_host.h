@@ -50,6 +50,7 @@ namespace mrh {
     cudaEvent_t consumed[2]{}; // on the compute stream, after the last frame that read d_buf[w]
     int which   = 0;
     bool active = false; // d_buf[which] holds the current frame's data
+    bool pending_direct = false; // a transfer straight from the caller's pinned memory is in flight
   };
 
 } // namespace mrh
@@ -75,6 +76,7 @@ struct mrh_map {
   mrh::Ingest in_depth, in_rgb, in_points;
   const float* depth_ptr = nullptr;
   const uint8_t* rgb_ptr = nullptr;
+  cudaEvent_t rgb_ready  = nullptr; // set by compute(): the colour image is only needed by the fusion kernels
   int depth_rows = 0, depth_cols = 0, rgb_rows = 0, rgb_cols = 0;
   size_t n_points = 0;
   float* d_points = nullptr;
@@ -93,13 +95,14 @@ struct mrh_map {
   double kernel_ms[8]{};
   uint64_t kernel_launches[8]{};
 
-  // point-cloud path staging: (voxel address, point index) keys + sdf values, double buffered for the sort
-  unsigned long long* d_upd_keys[2]{};
+  // point-cloud path staging: voxel-address keys (u32 or u64) + sdf values, `upd_slots` per point,
+  // double buffered for the sort
+  void* d_upd_keys[2]{};
   float* d_upd_vals[2]{};
   size_t upd_cap       = 0;
+  uint32_t upd_slots   = 0;
   void* d_sort_tmp     = nullptr;
   size_t sort_tmp_bytes = 0;
-  uint32_t* h_n_updates = nullptr; // pinned
 
   // meshing
   float* d_tri           = nullptr;
@@ -108,6 +111,10 @@ struct mrh_map {
   size_t soup_in_tri     = 0;       // triangles of the last marching-cubes run, still in d_tri
   float* d_soup_acc      = nullptr; // soups of earlier regions of the same extraction
   size_t soup_acc_n = 0, soup_acc_cap = 0;
+  // sharded meshing: ghost copies of other ranks' blocks sit behind entry halo_owned of the live list
+  bool halo_active       = false;
+  uint32_t halo_owned    = 0;
+  uint16_t* d_shell_idx  = nullptr;
   mrh::HostStore store;
   mrh::HostMesh mesh;
   // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel, device weld + D2H of the mesh, PLY

@@ -129,7 +129,7 @@ namespace {
     return 0;
   }
 
-  int run_marching_cubes(mrh_map* m, int force_generic) {
+  int run_marching_cubes(mrh_map* m, int force_generic, uint32_t max_centers = 0xFFFFFFFFu) {
     if (stash_soup(m))
       return 1;
     if (m->max_num_triangles > m->d_tri_cap) {
@@ -144,7 +144,7 @@ namespace {
     const double t0 = now_ms();
     CK(cudaMemsetAsync(m->d_tri_count, 0, sizeof(uint32_t), m->stream));
     const uint32_t cap = (uint32_t) std::min<uint64_t>(m->max_num_triangles, 0xFFFFFFFFull);
-    k_mc_blocks<<<m->num_sms * 4, 256, 0, m->stream>>>(m->dev, m->live_cur, m->d_tri, m->d_tri_count, cap, force_generic);
+    k_mc_blocks<<<m->num_sms * 4, 256, 0, m->stream>>>(m->dev, m->live_cur, m->d_tri, m->d_tri_count, cap, force_generic, max_centers);
     m->launches++;
     CK(cudaGetLastError());
     uint32_t n = 0;
@@ -268,6 +268,54 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
 
 int mrh_extract_mesh(mrh_map* m, const char* path) {
   return mrh_extract_mesh_ex(m, path, 0);
+}
+
+// ---- sharded meshing: mesh the blocks this handle owns where they are ----
+int mrh_mesh_local(mrh_map* m, size_t* n_triangles) {
+  if (!m || !n_triangles)
+    return fail("null argument");
+  CK(cudaSetDevice(m->device));
+  *n_triangles = 0;
+  m->mesh.clear();
+  m->soup_in_tri = m->soup_acc_n = 0;
+  if (m->max_num_triangles == 0)
+    return fail("mrh_mesh_local: max_num_triangles is 0");
+  if (run_marching_cubes(m, 0, m->halo_active ? m->halo_owned : 0xFFFFFFFFu))
+    return 1;
+  *n_triangles = m->soup_in_tri;
+  return 0;
+}
+
+int mrh_copy_triangles_device(mrh_map* m, float* d_dst, size_t cap_triangles) {
+  if (!m)
+    return fail("null handle");
+  CK(cudaSetDevice(m->device));
+  size_t n_tri      = 0;
+  const float* soup = device_soup(m, n_tri);
+  if (n_tri > cap_triangles)
+    return fail("mrh_copy_triangles_device: %zu triangles do not fit %zu", n_tri, cap_triangles);
+  if (n_tri) {
+    if (!d_dst)
+      return fail("null argument");
+    CK(cudaMemcpyAsync(d_dst, soup, sizeof(float) * 18 * n_tri, cudaMemcpyDeviceToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+  }
+  return 0;
+}
+
+int mrh_weld_device_soup(mrh_map* m, const float* d_soup, size_t n_triangles, const char* path) {
+  if (!m || (n_triangles && !d_soup))
+    return fail("null argument");
+  CK(cudaSetDevice(m->device));
+  const double t0 = now_ms();
+  if (weld_on_device(m, d_soup, n_triangles, (double) m->p.vertices_merging_threshold))
+    return 1;
+  m->mesh_ms_merge = now_ms() - t0;
+  const double t1  = now_ms();
+  if (path)
+    write_mesh_ply(path, m->mesh);
+  m->mesh_ms_ply = now_ms() - t1;
+  return 0;
 }
 
 int mrh_get_mesh(mrh_map* m, const double** v, const int32_t** f, const double** c, size_t* nv, size_t* nf) {

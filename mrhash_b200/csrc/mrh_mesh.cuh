@@ -285,7 +285,9 @@ __device__ __forceinline__ void mc_emit(const CellResult& c, float* tri_out /* n
 
 // One CTA (256 threads, 2 voxels each) per live block.
 // force_generic: run every block through the hash sampler (validation of the halo path).
-__global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, float* __restrict__ triangles, uint32_t* __restrict__ tri_count, uint32_t max_triangles, int force_generic) {
+// max_centers: only the first max_centers entries of the live list are meshed; the entries behind
+// them are ghost copies of other ranks' blocks (mrh_halo.cu), present only to be sampled.
+__global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, float* __restrict__ triangles, uint32_t* __restrict__ tri_count, uint32_t max_triangles, int force_generic, uint32_t max_centers) {
   __shared__ float s_sdf[1000];
   __shared__ uint32_t s_cw[1000];
   __shared__ uint32_t s_nb[27];
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
   __shared__ uint32_t s_warp_sum[8];
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_live = m.ctr->live_count[live_cur];
+  const uint32_t n_live = min(m.ctr->live_count[live_cur], max_centers);
   for (uint32_t li = blockIdx.x; li < n_live; li += gridDim.x) {
     const LiveEntry le = m.live[live_cur][li];
     if (le.slot == kInvalid)

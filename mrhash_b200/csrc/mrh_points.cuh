@@ -4,9 +4,11 @@
 // (:1215-1379). The reference updates voxels with a plain load / modify / store from one thread per
 // point, so several points racing on one voxel make its output run-to-run nondeterministic
 // (SURVEY.md H3). Here the walk and the update are split:
-//   k_points_emit  : one thread per point walks its voxel DDA and emits (voxel address, point
-//                    index, sdf) records - the set of records does not depend on voxel contents;
-//   (radix sort by (voxel address, point index))
+//   k_points_emit  : one thread per point walks its voxel DDA and writes (voxel address, sdf)
+//                    records into the point's own fixed run of slots (point-major order, unused
+//                    slots keep the all-ones hole key) - the records do not depend on voxel contents;
+//   (STABLE radix sort by voxel address: equal addresses stay in point order, holes sink to the end;
+//    the item count is points x slots, known on the host, so the frame needs no read-back)
 //   k_points_apply : one thread per distinct voxel folds its records in point order.
 // The result is deterministic and equals the reference's semantics with the points applied one
 // after another in index order (the CPU oracle's order).
@@ -15,7 +17,6 @@
 
 namespace mrh {
 
-constexpr int kPointIdxBits = 24; // up to 16.7 M points per cloud
 
 // ray end points of one point (shared by the allocation and integration walks)
 // for_alloc: allocBlocks3DKernel :939-961; else integrate3DKernel :1229-1250 (projective sdf)
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, Came
 }
 
 // One thread per point: voxel-level DDA, one record per visited voxel of an allocated block.
-__global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const float* __restrict__ points, uint32_t n_points, unsigned long long* __restrict__ keys, float* __restrict__ vals, uint32_t capacity) {
+// K = uint32_t while the pool address (+ hole key) fits 32 bits, else unsigned long long.
+template <typename K>
+__global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const float* __restrict__ points, uint32_t n_points, K* __restrict__ keys, float* __restrict__ vals, uint32_t slots) {
   __shared__ PoseDev pose;
   if (threadIdx.x == 0)
     load_pose(f, pose);
@@ -91,6 +94,9 @@ __global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const
     return;
   DDA dda;
   dda.init(a, b, m.voxel_size, m.ext, false);
+  K* my_keys     = keys + (size_t) i * slots;
+  float* my_vals = vals + (size_t) i * slots;
+  uint32_t n_out = 0, n_lost = 0;
   // consecutive voxels of a ray mostly share a block: remember the last lookup
   i3 last_b         = {INT_MIN, 0, 0};
   uint32_t last_val = kInvalid;
@@ -118,15 +124,19 @@ __global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const
       lx += lx < 0 ? 8 : 0, ly += ly < 0 ? 8 : 0, lz += lz < 0 ? 8 : 0;
       lx >>= r, ly >>= r, lz >>= r;
       const unsigned long long addr = (r ? (unsigned long long) (last_val & 0x7FFFFFFFu) * 64ull : (unsigned long long) last_val * 512ull) + (unsigned long long) (lz * 64 + ly * 8 + lx);
-      const uint32_t o              = atomicAdd(&m.ctr->n_updates, 1u);
-      if (o < capacity) {
-        keys[o] = (addr << kPointIdxBits) | (unsigned long long) i;
-        vals[o] = sdf;
+      if (n_out < slots) {
+        my_keys[n_out] = (K) addr;
+        my_vals[n_out] = sdf;
+        ++n_out;
+      } else {
+        ++n_lost;
       }
     }
     if (!dda.advance())
       break;
   }
+  if (n_lost)
+    atomicAdd(&m.ctr->dropped_updates, (unsigned long long) n_lost);
 }
 
 // pointers to the three words of the voxel at a reference pool address (see read_voxel_addr)
@@ -149,24 +159,26 @@ __device__ __forceinline__ bool voxel_words(const MapDev& m, unsigned long long 
   return true;
 }
 
-// One thread per run of equal voxel address in the sorted record list.
-__global__ void __launch_bounds__(256) k_points_apply(MapDev m, const unsigned long long* __restrict__ keys, const float* __restrict__ vals, uint32_t capacity) {
-  const uint32_t n = min(m.ctr->n_updates, capacity);
+// One thread per run of equal voxel address in the sorted record list (holes sorted to the end).
+template <typename K>
+__global__ void __launch_bounds__(256) k_points_apply(MapDev m, const K* __restrict__ keys, const float* __restrict__ vals, uint32_t n, K hole) {
   const float half = fmul(m.voxel_size, 0.5f);
   const float wn_f = __uint2float_rn((uint32_t) m.weight_sample);
   unsigned long long updated = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned long long addr = keys[i] >> kPointIdxBits;
-    if (i > 0 && (keys[i - 1] >> kPointIdxBits) == addr)
+    const K addr = keys[i];
+    if (addr == hole)
+      break; // everything from here on is a hole, for this thread's later iterations too
+    if (i > 0 && keys[i - 1] == addr)
       continue; // not the head of its run
     float *psdf, *pss;
     uint32_t* pcw;
-    if (!voxel_words(m, addr, psdf, pss, pcw))
+    if (!voxel_words(m, (unsigned long long) addr, psdf, pss, pcw))
       continue;
     float sdf0  = *psdf;
     float ss0   = *pss;
     uint32_t cw = *pcw;
-    for (uint32_t j = i; j < n && (keys[j] >> kPointIdxBits) == addr; ++j) {
+    for (uint32_t j = i; j < n && keys[j] == addr; ++j) {
       // integrate3DKernel :1333-1357 + combineVoxel (voxel_hash_utils.cuh:169-181), no colour input
       const float sdf       = vals[j];
       const uint32_t w0     = cw >> 24;
@@ -195,11 +207,8 @@ __global__ void __launch_bounds__(256) k_points_apply(MapDev m, const unsigned l
     updated += __shfl_xor_sync(0xFFFFFFFFu, updated, o);
   if ((threadIdx.x & 31) == 0 && updated)
     atomicAdd(&m.ctr->voxels_updated, updated);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&m.ctr->blocks_visible, (unsigned long long) m.ctr->vis_count);
-    if (m.ctr->n_updates > capacity)
-      atomicAdd(&m.ctr->dropped_updates, (unsigned long long) (m.ctr->n_updates - capacity));
-  }
 }
 
 } // namespace mrh

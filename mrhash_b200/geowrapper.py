@@ -79,6 +79,7 @@ class GeoWrapper:
         h = C.c_void_p()
         check(self._lib.mrh_create(C.byref(p), C.byref(h)))
         self._h = h
+        self._device = int(self._get("Device"))
         self._points = np.zeros((0, 3), np.float32)
         self._normals = np.zeros((0, 3), np.float32)
         self._extra = {}
@@ -245,16 +246,20 @@ class GeoWrapper:
             if nrm.shape[0] != pts.shape[0]:
                 raise RuntimeError("GeoWrapper::setPointCloud|point_cloud input and normals input should have the same number of points")
             nrm = _f32(nrm)
-        self._points = pts[:, :3].copy()
-        self._normals = nrm[:, :3].copy() if nrm is not None else np.zeros((pts.shape[0], 3), np.float32)
-        p = np.ascontiguousarray(self._points)
+        # the C side copies the points (staging buffer); the wrapper keeps references for the getters
+        # (getPointCloud / getNormals hand out copies) instead of two more 1.5 MB copies per frame
+        p = np.ascontiguousarray(pts[:, :3])
+        self._points = p
+        self._normals = np.ascontiguousarray(nrm[:, :3]) if nrm is not None else None
         check(self._lib.mrh_set_points(self._h, p.ctypes.data, p.shape[0], self._normals.ctypes.data if nrm is not None else None))
 
     def getPointCloud(self):
-        return self._points.copy()
+        return np.array(self._points, copy=True)
 
     def getNormals(self):
-        return self._normals.copy()
+        if self._normals is None:
+            return np.zeros((self._points.shape[0], 3), np.float32)
+        return np.array(self._normals, copy=True)
 
     # ---- the hot path ----
     def compute(self):
@@ -365,6 +370,62 @@ class GeoWrapper:
 
     def setShard(self, shard_rank, shard_world):
         check(self._lib.mrh_set_shard(self._h, int(shard_rank), int(shard_world)))
+
+    # ---- sharded meshing: boundary exchange (include/mrhash_b200.h, csrc/mrh_halo.cu). The tensors
+    # are torch CUDA tensors on this handle's device; torch is only the buffer / NCCL plumbing. ----
+    def haloRecordBytes(self, full):
+        return int(self._lib.mrh_halo_record_bytes(int(bool(full))))
+
+    def haloRequests(self):
+        """int32 [n,3] keys of the blocks next to owned blocks that another rank owns (unique)."""
+        import torch
+
+        dev = torch.device("cuda", self._device)
+        cap = max(1024, 8 * self.getStats()["live_blocks"])
+        while True:
+            keys = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+            n = C.c_size_t()
+            check(self._lib.mrh_halo_requests(self._h, keys.data_ptr(), cap, C.byref(n)))
+            if n.value <= cap:
+                return keys[: n.value]
+            cap = n.value
+
+    def haloPack(self, keys, full):
+        """Owner side: uint8 [n, haloRecordBytes(full)] records for int32 [n,3] keys."""
+        import torch
+
+        keys = keys.contiguous()
+        out = torch.empty((len(keys), self.haloRecordBytes(full)), dtype=torch.uint8, device=keys.device)
+        check(self._lib.mrh_halo_pack(self._h, keys.data_ptr(), len(keys), int(bool(full)), out.data_ptr()))
+        return out
+
+    def haloInsert(self, keys, records, full):
+        keys, records = keys.contiguous(), records.contiguous()
+        assert len(keys) == len(records)
+        check(self._lib.mrh_halo_insert(self._h, keys.data_ptr(), records.data_ptr(), len(keys), int(bool(full))))
+
+    def haloClear(self):
+        check(self._lib.mrh_halo_clear(self._h))
+
+    def meshLocal(self):
+        """Marching cubes over the owned blocks in place; returns the soup as a torch CUDA tensor [T,3,6]."""
+        import torch
+
+        n = C.c_size_t()
+        check(self._lib.mrh_mesh_local(self._h, C.byref(n)))
+        soup = torch.empty((n.value, 3, 6), dtype=torch.float32, device=torch.device("cuda", self._device))
+        check(self._lib.mrh_copy_triangles_device(self._h, soup.data_ptr(), n.value))
+        return soup
+
+    def weldSoup(self, soup, filename=None):
+        """processTriangles + PLY over a soup tensor [T,3,6] on this handle's device; mesh via getVertices/..."""
+        soup = soup.contiguous()
+        check(self._lib.mrh_weld_device_soup(self._h, soup.data_ptr(), len(soup), filename.encode() if filename else None))
+
+    def hasLowResolutionBlocks(self):
+        """True when the map may hold resolution-1 blocks (then whole blocks are exchanged, not shells)."""
+        self.getStats()  # refreshes the counters the field reads
+        return bool(self._get("LowResolutionBlocks"))
 
     def dumpState(self):
         """(entries [n,5] int32 = x,y,z,resolution,ptr sorted by key; voxels structured [n,512])."""

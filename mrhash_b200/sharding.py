@@ -5,8 +5,11 @@ GPU g of G owns the block keys whose reference hash bucket (calculateHash,
 [g*nb/G, (g+1)*nb/G). Every rank sees the whole frame (rank 0 ingests it and broadcasts it), walks
 all rays, but inserts / fuses / collects only the blocks it owns, so integration needs no exchange:
 a voxel update depends only on the frame and the voxel's own state. Meshing reads the 26 neighbour
-blocks, which under hash partitioning live on other ranks: blocks are exchanged once before it
-(`gather_blocks`).
+blocks, which under hash partitioning live on other ranks: before it, every rank fetches the
+one-voxel shells of the neighbour blocks it does not own from their owners (`halo_exchange`, two
+all-to-alls: 12-byte keys out, ~2.4 KB records back), meshes its own blocks in place, and only the
+triangle soups are gathered for the weld (`extract_mesh_sharded`). `gather_blocks` /
+`extract_mesh_gathered` is the older variant that ships whole shards to one rank.
 
 torch.distributed is plumbing only (NCCL on the GPU box, gloo in the CPU tests).
 """
@@ -85,7 +88,98 @@ def gather_blocks(entries, voxels, dst=0, group=None, device="cpu"):
     return ee[order], vv[order]
 
 
-def extract_mesh_sharded(geo, path, dst=0, group=None, device="cpu"):
+def owner_of_torch(keys, world, num_buckets):
+    """owner_of for an int32 tensor [n,3] (any device), same arithmetic, in torch int64."""
+    import torch
+
+    k = keys.to(torch.int64) & 0xFFFFFFFF
+    h = ((k[:, 0] * P0) & 0xFFFFFFFF) ^ ((k[:, 1] * P1) & 0xFFFFFFFF) ^ ((k[:, 2] * P2) & 0xFFFFFFFF)
+    h = h % int(num_buckets)
+    if world <= 1:
+        return torch.zeros_like(h)
+    bounds = torch.tensor([bucket_range(r, world, num_buckets)[1] for r in range(world)], dtype=torch.int64, device=keys.device)
+    return torch.searchsorted(bounds, h, right=True)
+
+
+def _all_to_all_rows(rows, send_counts, group=None):
+    """Variable-size all-to-all of the rows of a 2-D tensor (rows grouped by destination rank).
+    Returns (received rows, receive counts)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=rows.device)
+    rc = torch.empty(world, dtype=torch.int64, device=rows.device)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    out = torch.empty((sum(recv_counts),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
+    return out, recv_counts
+
+
+def halo_exchange(geo, group=None):
+    """Boundary exchange before meshing a sharded map. `geo` needs haloRequests(),
+    haloPack(keys, full), haloInsert(keys, records, full), hasLowResolutionBlocks(),
+    getHashNumBuckets(); tensors live wherever haloRequests() puts them (CUDA with NCCL, CPU with
+    gloo in the tests). Returns a dict of what was moved."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    nb = int(geo.getHashNumBuckets())
+    req = geo.haloRequests()
+    # whole blocks instead of shells as soon as any rank holds resolution-1 blocks
+    flag = torch.tensor([1 if geo.hasLowResolutionBlocks() else 0], dtype=torch.int64, device=req.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    full = bool(int(flag.item()))
+    owner = owner_of_torch(req, world, nb)
+    order = torch.argsort(owner, stable=True)
+    req = req[order].contiguous()
+    send_counts = torch.bincount(owner, minlength=world).tolist()
+    asked, asked_counts = _all_to_all_rows(req, send_counts, group)  # keys other ranks want from me
+    records = geo.haloPack(asked, full)
+    got, got_counts = _all_to_all_rows(records, asked_counts, group)  # answers, in the order I asked
+    assert got_counts == [int(c) for c in send_counts] and len(got) == len(req)
+    geo.haloInsert(req, got, full)
+    return {"requested": int(len(req)), "served": int(len(asked)), "full_blocks": full, "bytes_received": int(got.numel()), "bytes_sent": int(records.numel())}
+
+
+def extract_mesh_sharded(geo, path, dst=0, group=None):
+    """extractMesh for a hash-sharded map without moving the shards: boundary exchange, marching
+    cubes over the owned blocks on every rank, gather of the triangle soups on `dst`, weld + PLY
+    there. Returns (True, info) on dst, (False, info) elsewhere. The maps stay on their devices."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        geo.extractMesh(path)
+        return True, {}
+    info = halo_exchange(geo, group)
+    try:
+        soup = geo.meshLocal()
+    finally:
+        geo.haloClear()
+    n = torch.tensor([len(soup)], dtype=torch.int64, device=soup.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    info["triangles_local"] = counts[rank]
+    n_max = max(counts + [1])
+    padded = torch.zeros((n_max, 3, 6), dtype=torch.float32, device=soup.device)
+    padded[: len(soup)] = soup
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, parts, dst=dst, group=group)
+    if rank != dst:
+        return False, info
+    whole = torch.cat([parts[r][: counts[r]] for r in range(world)])
+    info["triangles_total"] = int(len(whole))
+    geo.weldSoup(whole, path)
+    return True, info
+
+
+def extract_mesh_gathered(geo, path, dst=0, group=None, device="cpu"):
     """extractMesh for a hash-sharded map: every rank hands its blocks to `dst` (one gather over the
     process group), which streams all of them into its own handle and meshes the whole map, so
     neighbour look-ups never cross a shard boundary. Returns True on `dst`. The shards stay as they

@@ -84,3 +84,129 @@ def test_sharded_map_meshes_like_the_unsharded_one():
     ka = np.sort(np.ascontiguousarray(ta.reshape(len(ta), -1)).view([("", ta.dtype)] * 18).ravel())
     kw = np.sort(np.ascontiguousarray(tw.reshape(len(tw), -1)).view([("", tw.dtype)] * 18).ravel())
     assert (ka == kw).all()
+
+
+def _sorted_soup(t):
+    t = np.ascontiguousarray(np.asarray(t).reshape(len(t), -1))
+    return np.sort(t.view([("", t.dtype)] * 18).ravel())
+
+
+def _exchange_in_process(shards, world, full=None):
+    """What sharding.halo_exchange does over NCCL, with every rank's handle in this process."""
+    import torch
+
+    if full is None:
+        full = any(g.hasLowResolutionBlocks() for g in shards)
+    moved = 0
+    for r, g in enumerate(shards):
+        req = g.haloRequests()
+        owner = sharding.owner_of_torch(req, world, NUM_BUCKETS)
+        assert len(req) > 0 and not bool((owner == r).any())
+        assert len(torch.unique(req, dim=0)) == len(req)
+        keys, recs = [], []
+        for o in range(world):
+            k = req[owner == o].contiguous()
+            keys.append(k)
+            recs.append(shards[o].haloPack(k, full))
+        keys, recs = torch.cat(keys), torch.cat(recs)
+        assert recs.shape[1] == g.haloRecordBytes(full)
+        g.haloInsert(keys, recs, full)
+        moved += recs.numel()
+    return moved
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_meshes_shards_in_place(world):
+    """Boundary exchange (csrc/mrh_halo.cu): every shard receives the one-voxel shells of the
+    neighbour blocks it does not own, meshes ONLY its own blocks, and the union of the shard soups
+    is the unsharded soup, triangle for triangle, bit for bit. Afterwards the ghosts are gone."""
+    import torch
+
+    p = dict(synth.REPLICA_PARAMS)
+    w, h = 320, 240
+    fx, fy, cx, cy = synth.intrinsics(w, h)
+
+    def mk(rank, n):
+        g = GeoWrapper(**p, num_sdf_blocks=NUM_BLOCKS, hash_num_buckets=NUM_BUCKETS, max_num_triangles=1_000_000, shard_rank=rank, shard_world=n)
+        g.setCamera(fx, fy, cx, cy, h, w, p["min_depth"], p["max_depth"], 0)
+        return g
+
+    whole = mk(0, 1)
+    shards = [mk(r, world) for r in range(world)]
+    for k in range(6):
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000, width=w, height=h)
+        for g in [whole] + shards:
+            g.setCurrPose(t, q)
+            g.setDepthImage(depth)
+            g.setRGBImage(rgb)
+            g.compute()
+    before = [(g.dumpState(), g.getStats()) for g in shards]
+    whole_soup = whole.meshLocal().cpu().numpy()
+    assert len(whole_soup) > 1000
+    moved = _exchange_in_process(shards, world)
+    soups = [g.meshLocal().cpu().numpy() for g in shards]
+    assert all(len(s) > 0 for s in soups)
+    for g in shards:
+        g.haloClear()
+    union = np.concatenate(soups)
+    print(f"[halo world={world}] triangles {[len(s) for s in soups]} = {len(union)} (unsharded {len(whole_soup)}), {moved / 1e6:.1f} MB of shell records exchanged")
+    assert len(union) == len(whole_soup)
+    assert (_sorted_soup(union) == _sorted_soup(whole_soup)).all()
+    # without the exchange the shard soups lose the triangles next to foreign blocks
+    lonely = np.concatenate([g.meshLocal().cpu().numpy() for g in shards])
+    assert len(lonely) < len(whole_soup)
+    # the maps are exactly what they were
+    for g, ((e0, v0), st0) in zip(shards, before):
+        e1, v1 = g.dumpState()
+        st1 = g.getStats()
+        assert np.array_equal(e0[:, :4], e1[:, :4]) and v0.tobytes() == v1.tobytes()
+        assert st1["heap_free"] == st0["heap_free"] and st1["live_blocks"] == st0["live_blocks"] and st1["blocks_new"] == st0["blocks_new"]
+    # the weld of the gathered soups is a closed index set over unique vertices
+    g0 = shards[0]
+    g0.weldSoup(torch.from_numpy(union).cuda())
+    V, F = g0.getVertices(), g0.getFaces()
+    assert len(np.unique(V, axis=0)) == len(V) and F.max() < len(V)
+    whole.weldSoup(torch.from_numpy(whole_soup).cuda())
+    assert len(whole.getVertices()) == len(V) and len(whole.getFaces()) == len(F)
+    # integration continues normally after the exchange
+    t, q, depth, rgb = synth.rgbd_frame(6, n_frames=2000, width=w, height=h)
+    for g in [whole] + shards:
+        g.setCurrPose(t, q), g.setDepthImage(depth), g.setRGBImage(rgb), g.compute()
+    parts = [g.dumpState() for g in shards]
+    ee = np.concatenate([e for e, _ in parts])
+    vv = np.concatenate([v for _, v in parts])
+    order = np.lexsort((ee[:, 2], ee[:, 1], ee[:, 0]))
+    assert compare_dumps((ee[order], vv[order]), whole.dumpState())["ok"]
+
+
+def test_halo_exchange_with_resolution1_blocks_ships_whole_blocks():
+    """Variance path on: ghosts may be resolution-1 blocks, records carry whole blocks. The mixed-
+    resolution sampler reads pool neighbours, so only coverage is asserted."""
+    p = dict(synth.REPLICA_PARAMS)
+    p["sdf_var_threshold"] = 0.03
+    w, h = 320, 240
+    fx, fy, cx, cy = synth.intrinsics(w, h)
+
+    def mk(rank, n):
+        g = GeoWrapper(**p, num_sdf_blocks=NUM_BLOCKS, hash_num_buckets=NUM_BUCKETS, max_num_triangles=1_000_000, shard_rank=rank, shard_world=n)
+        g.setCamera(fx, fy, cx, cy, h, w, p["min_depth"], p["max_depth"], 0)
+        return g
+
+    whole, shards = mk(0, 1), [mk(0, 2), mk(1, 2)]
+    for k in range(7):
+        t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000, width=w, height=h)
+        for g in [whole] + shards:
+            g.setCurrPose(t, q), g.setDepthImage(depth), g.setRGBImage(rgb), g.compute()
+    n_low = int((whole.dumpState()[0][:, 3] == 1).sum())
+    assert all(g.hasLowResolutionBlocks() for g in shards)
+    free0 = [(g.getStats()["heap_free"], g.getStats()["heap_low_free"]) for g in shards]
+    _exchange_in_process(shards, 2)
+    n = sum(len(g.meshLocal()) for g in shards)
+    for g in shards:
+        g.haloClear()
+    n_whole = len(whole.meshLocal())
+    print(f"[halo + variance] resolution-1 blocks {n_low}, triangles sharded {n} vs unsharded {n_whole}")
+    assert n_whole > 1000 and abs(n - n_whole) <= 0.02 * n_whole
+    for g, (fh, fl) in zip(shards, free0):
+        st = g.getStats()
+        assert st["heap_free"] + st["heap_low_free"] // 8 >= fh - 8 and st["live_blocks"] > 0

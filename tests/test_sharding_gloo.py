@@ -59,6 +59,101 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+class _FakeShard:
+    """numpy stand-in for a sharded GeoWrapper: owns the blocks of its bucket range out of a common
+    random set; a block's record payload is derived from its key, so every answer can be checked."""
+
+    REC = 32
+
+    def __init__(self, blocks, rank, world, nb):
+        self.rank, self.world, self.nb = rank, world, nb
+        self.all = blocks
+        self.own = {tuple(b) for b in blocks[sharding.owner_of(blocks, world, nb) == rank].tolist()}
+        self.ghosts = {}
+
+    def getHashNumBuckets(self):
+        return self.nb
+
+    def hasLowResolutionBlocks(self):
+        return self.rank == 1  # one rank holding resolution-1 blocks switches everybody to full records
+
+    def haloRequests(self):
+        want = set()
+        for b in self.own:
+            for dx in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    for dz in (-1, 0, 1):
+                        k = (b[0] + dx, b[1] + dy, b[2] + dz)
+                        if k != b and sharding.owner_of(np.array([k]), self.world, self.nb)[0] != self.rank:
+                            want.add(k)
+        return torch.tensor(sorted(want), dtype=torch.int32).reshape(-1, 3)
+
+    @staticmethod
+    def payload(key, owner):
+        return np.array([1, owner, key[0] & 0xFF, key[1] & 0xFF, key[2] & 0xFF], np.int32)
+
+    def haloPack(self, keys, full):
+        assert full
+        out = torch.zeros((len(keys), self.REC), dtype=torch.uint8)
+        for i, k in enumerate(keys.tolist()):
+            assert sharding.owner_of(np.array([k]), self.world, self.nb)[0] == self.rank  # routed to the owner
+            rec = self.payload(k, self.rank) if tuple(k) in self.own else np.array([-1, 0, 0, 0, 0], np.int32)
+            out[i, :20] = torch.from_numpy(rec.view(np.uint8))
+        return out
+
+    def haloInsert(self, keys, records, full):
+        for k, r in zip(keys.tolist(), records.numpy()):
+            self.ghosts[tuple(k)] = r[:20].view(np.int32).copy()
+
+
+def _halo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        blocks = np.unique(rng.integers(-6, 6, size=(300, 3)), axis=0).astype(np.int32)
+        nb = 997
+        g = _FakeShard(blocks, rank, world, nb)
+        info = sharding.halo_exchange(g)
+        assert info["full_blocks"] and info["requested"] == len(g.ghosts) > 0
+        present = {tuple(b) for b in blocks.tolist()}
+        n_found = 0
+        for k, rec in g.ghosts.items():
+            owner = int(sharding.owner_of(np.array([k]), world, nb)[0])
+            assert owner != rank
+            if k in present:
+                assert np.array_equal(rec, _FakeShard.payload(k, owner)), (k, rec)
+                n_found += 1
+            else:
+                assert rec[0] == -1
+        assert n_found > 0
+        # owner_of_torch == owner_of
+        assert np.array_equal(sharding.owner_of_torch(torch.from_numpy(blocks), world, nb).numpy(), sharding.owner_of(blocks, world, nb))
+        out.put((rank, "ok"))
+    except Exception as exc:  # pragma: no cover
+        import traceback
+
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_routing_world2():
+    """Both all-to-alls of sharding.halo_exchange over gloo: every requested key reaches its owner
+    and the owner's answer (or "not held") comes back to the rank that asked, in request order."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert results == {0: "ok", 1: "ok"}, results
+
+
 def test_partition_and_exchange_world2():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
