@@ -127,11 +127,11 @@ def make_stream(args, n, device):
     return depth, rgb, poses
 
 
-def new_map(args, rank, world, device_index):
+def new_map(args, rank, world, device_index, max_num_triangles=1):
     from mrhash_b200 import GeoWrapper, synth
 
     p = dict(synth.REPLICA_PARAMS)
-    g = GeoWrapper(**p, num_sdf_blocks=NUM_SDF_BLOCKS, hash_num_buckets=HASH_NUM_BUCKETS, max_num_triangles=1, device=device_index, shard_rank=rank, shard_world=world)
+    g = GeoWrapper(**p, num_sdf_blocks=NUM_SDF_BLOCKS, hash_num_buckets=HASH_NUM_BUCKETS, max_num_triangles=max_num_triangles, device=device_index, shard_rank=rank, shard_world=world)
     fx, fy, cx, cy = synth.intrinsics(args.width, args.height)
     g.setCamera(fx, fy, cx, cy, args.height, args.width, p["min_depth"], p["max_depth"], 0)
     return g
@@ -349,7 +349,7 @@ def main():
     depth_h.copy_(depth)
     rgb_h.copy_(rgb)
     depth_np, rgb_np = depth_h.numpy(), rgb_h.numpy()
-    g = new_map(args, rank, world, local)
+    g = new_map(args, rank, world, local, max_num_triangles=4_000_000 if world > 1 else 1)
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
     bcast_d = torch.empty((args.height, args.width), dtype=torch.float32, device=dev) if world > 1 else None
     bcast_c = torch.empty((args.height, args.width, 3), dtype=torch.uint8, device=dev) if world > 1 else None
@@ -412,6 +412,38 @@ def main():
     g_e2e = g  # NCCL enqueued work on this handle's stream: destroy it only after the process group
     if world == 1:
         g.close()
+
+    # ---------------- N > 1 only: (i) one independent stream per GPU, (ii) sharded meshing ------------
+    extra_multi = {}
+    if world > 1:
+        # (i) replicas: every rank maps its own copy of the stream, unsharded, no collective - the
+        # aggregate a multi-session server gets from the box (weak scaling of the same hot path)
+        g = new_map(args, 0, 1, local)
+        stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
+        for k in range(W):
+            step_device(k)
+        g.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        r0.record(stream)
+        for i in range(K):
+            step_device(W + i)
+        r1.record(stream)
+        g.synchronize()
+        barrier()
+        ms_rep = max_over_ranks(r0.elapsed_time(r1))
+        g.close()
+        extra_multi["replica_streams"] = {"value": world * K / (ms_rep * 1e-3), "unit": "frames/s", "scaling": "weak", "what": "one unsharded stream per GPU, L2 warm, aggregate over ranks"}
+        # (ii) meshing the sharded map of the e2e pass where it lies: boundary exchange (two NCCL
+        # all-to-alls), marching cubes per rank, soup gather + weld on rank 0
+        from mrhash_b200 import sharding
+
+        barrier()
+        t0 = time.perf_counter()
+        _, info = sharding.extract_mesh_sharded(g_e2e, None, dst=0)
+        barrier()
+        info["ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        extra_multi["sharded_mesh"] = info
 
     # ---------------- roofline pass: per-kernel CUDA-event times, L2 flushed ------------------------
     Kp = min(K, 200)
@@ -497,6 +529,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line.update(extra_multi)
         print(json.dumps(line))
     if world > 1:
         torch.cuda.synchronize()

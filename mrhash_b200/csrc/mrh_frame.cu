@@ -260,10 +260,12 @@ int integrate_points(mrh_map* m) {
   const FrameDev& f  = c.f;
   cudaStream_t s     = m->stream;
   const uint32_t n   = (uint32_t) m->n_points;
-  // record slots: a ray of length 2t crosses at most 3*(2t/size)+4 voxels; every point owns that many
-  // (the sort runs over points x slots items, a count the host knows without asking the device)
+  // record slots: a segment of length L = 2t visits at most L (|dx| + |dy| + |dz|) / size + 4 <=
+  // sqrt(3) L / size + 4 voxels (one per axis crossing plus the start, plus one per axis of rounding
+  // slack); every point owns that many slots, and the sort runs over points x slots items - a count
+  // the host knows without asking the device. Anything beyond would be counted in dropped_updates.
   const float t_max    = m->p.sdf_truncation + m->p.sdf_truncation_scale * m->max_integration_distance;
-  const size_t per_pt  = (size_t) std::min(3.0 * std::ceil(2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
+  const size_t per_pt  = (size_t) std::min(std::ceil(1.7320508 * 2.0 * t_max / m->p.virtual_voxel_size) + 4.0, 256.0);
   const size_t max_items = (size_t) 1 << 28;
   const size_t slots   = std::max<size_t>(1, std::min(per_pt, max_items / std::max<size_t>(n, 1)));
   const size_t want    = (size_t) n * slots;

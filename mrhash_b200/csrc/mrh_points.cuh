@@ -159,53 +159,77 @@ __device__ __forceinline__ bool voxel_words(const MapDev& m, unsigned long long 
   return true;
 }
 
-// One thread per run of equal voxel address in the sorted record list (holes sorted to the end).
+// Folds the sorted records into the voxels: one lane per run of equal voxel address (holes sorted to
+// the end). A warp first finds the run heads of a 256-record tile with ballots and queues them in
+// shared memory, then its lanes take the queued runs round-robin - with ~5 records per run, one
+// thread per record would leave 4 of 5 lanes idle while the heads loop.
+constexpr int kApplyTile = 256; // records per warp tile
 template <typename K>
 __global__ void __launch_bounds__(256) k_points_apply(MapDev m, const K* __restrict__ keys, const float* __restrict__ vals, uint32_t n, K hole) {
+  __shared__ uint32_t s_heads[8][kApplyTile];
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float half = fmul(m.voxel_size, 0.5f);
   const float wn_f = __uint2float_rn((uint32_t) m.weight_sample);
   unsigned long long updated = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const K addr = keys[i];
-    if (addr == hole)
-      break; // everything from here on is a hole, for this thread's later iterations too
-    if (i > 0 && keys[i - 1] == addr)
-      continue; // not the head of its run
-    float *psdf, *pss;
-    uint32_t* pcw;
-    if (!voxel_words(m, (unsigned long long) addr, psdf, pss, pcw))
-      continue;
-    float sdf0  = *psdf;
-    float ss0   = *pss;
-    uint32_t cw = *pcw;
-    for (uint32_t j = i; j < n && keys[j] == addr; ++j) {
-      // integrate3DKernel :1333-1357 + combineVoxel (voxel_hash_utils.cuh:169-181), no colour input
-      const float sdf       = vals[j];
-      const uint32_t w0     = cw >> 24;
-      const float curr_mean = w0 > 0 ? sdf0 : 0.f;
-      const float delta     = fdiv(fsub(sdf, curr_mean), half);
-      const uint32_t wsum   = w0 + (uint32_t) m.weight_sample;
-      const float merged    = fdiv(ffma(sdf, wn_f, fmul(sdf0, __uint2float_rn(w0))), __uint2float_rn(wsum));
-      const uint32_t r0 = cw & 0xFF, g0 = (cw >> 8) & 0xFF, b0 = (cw >> 16) & 0xFF;
-      const uint32_t rr = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(r0), 0.5f)), 0.5f)) & 0xFF;
-      const uint32_t gg = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(g0), 0.5f)), 0.5f)) & 0xFF;
-      const uint32_t bb = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(b0), 0.5f)), 0.5f)) & 0xFF;
-      const uint32_t wn = min(wsum, (uint32_t) kWeightMax);
-      const float delta2 = fdiv(fsub(sdf, merged), half);
-      float ss           = fmul(delta, delta2);
-      if (fabsf(ss) < 1.175494350822287508e-38f)
-        ss = 0.f;
-      sdf0 = merged;
-      ss0  = fadd(0.f, ss);
-      cw   = rr | (gg << 8) | (bb << 16) | (wn << 24);
-      ++updated;
+  const uint32_t n_tiles     = (n + kApplyTile - 1) / kApplyTile;
+  for (uint32_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += gridDim.x * 8) {
+    const uint32_t base = tile * kApplyTile;
+    if (keys[base] == hole)
+      break; // sorted: nothing but holes from here on, for every later tile of this warp too
+    uint32_t n_heads = 0;
+#pragma unroll
+    for (int r = 0; r < kApplyTile / 32; ++r) {
+      const uint32_t i = base + r * 32 + lane;
+      const K k        = i < n ? keys[i] : hole;
+      const K prev     = i > 0 && i <= n ? keys[i - 1] : hole;
+      const bool head  = k != hole && (i == 0 || prev != k);
+      const unsigned hm = __ballot_sync(full, head);
+      if (head)
+        s_heads[warp][n_heads + __popc(hm & ((1u << lane) - 1u))] = i;
+      n_heads += __popc(hm);
     }
-    *psdf = sdf0, *pss = ss0, *pcw = cw;
+    __syncwarp();
+    for (uint32_t hq = lane; hq < n_heads; hq += 32) {
+      const uint32_t i = s_heads[warp][hq];
+      const K addr     = keys[i];
+      float *psdf, *pss;
+      uint32_t* pcw;
+      if (!voxel_words(m, (unsigned long long) addr, psdf, pss, pcw))
+        continue;
+      float sdf0  = *psdf;
+      float ss0   = *pss;
+      uint32_t cw = *pcw;
+      for (uint32_t j = i; j < n && keys[j] == addr; ++j) {
+        // integrate3DKernel :1333-1357 + combineVoxel (voxel_hash_utils.cuh:169-181), no colour input
+        const float sdf       = vals[j];
+        const uint32_t w0     = cw >> 24;
+        const float curr_mean = w0 > 0 ? sdf0 : 0.f;
+        const float delta     = fdiv(fsub(sdf, curr_mean), half);
+        const uint32_t wsum   = w0 + (uint32_t) m.weight_sample;
+        const float merged    = fdiv(ffma(sdf, wn_f, fmul(sdf0, __uint2float_rn(w0))), __uint2float_rn(wsum));
+        const uint32_t r0 = cw & 0xFF, g0 = (cw >> 8) & 0xFF, b0 = (cw >> 16) & 0xFF;
+        const uint32_t rr = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(r0), 0.5f)), 0.5f)) & 0xFF;
+        const uint32_t gg = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(g0), 0.5f)), 0.5f)) & 0xFF;
+        const uint32_t bb = (uint32_t) f2i(fadd(ffma(0.f, 0.5f, fmul(__uint2float_rn(b0), 0.5f)), 0.5f)) & 0xFF;
+        const uint32_t wn = min(wsum, (uint32_t) kWeightMax);
+        const float delta2 = fdiv(fsub(sdf, merged), half);
+        float ss           = fmul(delta, delta2);
+        if (fabsf(ss) < 1.175494350822287508e-38f)
+          ss = 0.f;
+        sdf0 = merged;
+        ss0  = fadd(0.f, ss);
+        cw   = rr | (gg << 8) | (bb << 16) | (wn << 24);
+        ++updated;
+      }
+      *psdf = sdf0, *pss = ss0, *pcw = cw;
+    }
+    __syncwarp();
   }
   // warp-aggregated statistics
   for (int o = 16; o > 0; o >>= 1)
     updated += __shfl_xor_sync(0xFFFFFFFFu, updated, o);
-  if ((threadIdx.x & 31) == 0 && updated)
+  if (lane == 0 && updated)
     atomicAdd(&m.ctr->voxels_updated, updated);
   if (blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&m.ctr->blocks_visible, (unsigned long long) m.ctr->vis_count);

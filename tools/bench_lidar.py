@@ -34,9 +34,18 @@ for thr in (0.0, 0.005):
     g.resetStats()
     l0 = g.launchCount()
     t0 = time.perf_counter()
+    host = [0.0, 0.0, 0.0]
     for T, pts in frames[warm:]:
-        g.setCurrPoseMatrix(T), g.setPointCloud(pts, False), g.compute()
+        c0 = time.perf_counter()
+        g.setCurrPoseMatrix(T), g.setPointCloud(pts, False)
+        c1 = time.perf_counter()
+        g.compute()
+        c2 = time.perf_counter()
         st = g.getStats()
+        c3 = time.perf_counter()
+        host[0] += c1 - c0
+        host[1] += c2 - c1
+        host[2] += c3 - c2
     dt = time.perf_counter() - t0
     row = {
         "frames_per_sec_e2e": n_frames / dt,
@@ -45,6 +54,7 @@ for thr in (0.0, 0.005):
         "voxel_updates_per_frame": st["voxels_updated"] / n_frames,
         "live_blocks_end": st["live_blocks"],
         "launches_per_frame": (g.launchCount() - l0) / n_frames,
+        "host_us_per_frame": {"setters": 1e6 * host[0] / n_frames, "compute": 1e6 * host[1] / n_frames, "read_result": 1e6 * host[2] / n_frames},
         "dropped": [st["dropped_heap"], st["dropped_table"], st["dropped_updates"]],
     }
     g.close()
