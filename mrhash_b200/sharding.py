@@ -101,6 +101,16 @@ def owner_of_torch(keys, world, num_buckets):
     return torch.searchsorted(bounds, h, right=True)
 
 
+def _wait(t):
+    """NCCL collectives are asynchronous on torch's stream; the C ABI works on the handle's own
+    stream. Wait for the collective that produced `t` before handing it to the library."""
+    if t.is_cuda:
+        import torch
+
+        torch.cuda.current_stream(t.device).synchronize()
+    return t
+
+
 def _all_to_all_rows(rows, send_counts, group=None):
     """Variable-size all-to-all of the rows of a 2-D tensor (rows grouped by destination rank).
     Returns (received rows, receive counts)."""
@@ -114,7 +124,7 @@ def _all_to_all_rows(rows, send_counts, group=None):
     recv_counts = [int(x) for x in rc.tolist()]
     out = torch.empty((sum(recv_counts),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
     dist.all_to_all_single(out, rows.contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(send_counts), group=group)
-    return out, recv_counts
+    return _wait(out), recv_counts
 
 
 def halo_exchange(geo, group=None):
@@ -173,7 +183,7 @@ def extract_mesh_sharded(geo, path, dst=0, group=None):
     dist.gather(padded, parts, dst=dst, group=group)
     if rank != dst:
         return False, info
-    whole = torch.cat([parts[r][: counts[r]] for r in range(world)])
+    whole = _wait(torch.cat([parts[r][: counts[r]] for r in range(world)]))
     info["triangles_total"] = int(len(whole))
     geo.weldSoup(whole, path)
     return True, info
