@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
 
     base = {"impl": "reference", "metric": "rgbd_frames_per_sec", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True}
     if not ref_available() or not torch.cuda.is_available():
-        print(json.dumps({**base, "unavailable": "oracle/_ref/libref_harness.so missing or no CUDA device"}))
+        print(json.dumps({**base, "unavailable": "oracle/_ref/libref_harness.so missing or no CUDA device"}), flush=True)
         return
     n = args.warmup + args.steps
     depth, rgb, poses = make_stream(args, n, "cuda:0")
@@ -235,10 +235,16 @@ def run_reference(args, rank, world):
         "clocks": sampler.summary([(w0, w1)]),
         "gpu_launches": None,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (the library's
+    # reference-style progress prints, NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -290,11 +296,20 @@ def main():
     g = new_map(args, rank, world, local)
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
 
+    from mrhash_b200 import sharding
+
+    def run_frame(geo):
+        # one rank of a sharded map: compute() plus, on starve frames, the z-buffer min-reduction
+        if world > 1 and geo.shardWorld() > 1:
+            sharding.compute_sharded(geo)
+        else:
+            geo.compute()
+
     def step_device(k):
         g.setCurrPose(*poses[k])
         g.setDepthImageDevice(depth[k].data_ptr(), args.height, args.width)
         g.setRGBImageDevice(rgb[k].data_ptr(), args.height, args.width)
-        g.compute()
+        run_frame(g)
 
     for k in range(W):
         step_device(k)
@@ -389,7 +404,7 @@ def main():
             stream.wait_event(ev_ready)
             g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
             g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
-            g.compute()
+            run_frame(g)
             ev_done.record(stream)
             return g.getStats()
 
@@ -436,13 +451,15 @@ def main():
         extra_multi["replica_streams"] = {"value": world * K / (ms_rep * 1e-3), "unit": "frames/s", "scaling": "weak", "what": "one unsharded stream per GPU, L2 warm, aggregate over ranks"}
         # (ii) meshing the sharded map of the e2e pass where it lies: boundary exchange (two NCCL
         # all-to-alls), marching cubes per rank, soup gather + weld on rank 0
-        from mrhash_b200 import sharding
-
         barrier()
         t0 = time.perf_counter()
+        sharding.extract_mesh_sharded(g_e2e, None, dst=0)  # first call: NCCL sets up its all-to-all peer connections
+        barrier()
+        t1 = time.perf_counter()
         _, info = sharding.extract_mesh_sharded(g_e2e, None, dst=0)
         barrier()
-        info["ms"] = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        info["ms"] = max_over_ranks((time.perf_counter() - t1) * 1e3)
+        info["ms_first_call"] = max_over_ranks((t1 - t0) * 1e3)
         extra_multi["sharded_mesh"] = info
 
     # ---------------- roofline pass: per-kernel CUDA-event times, L2 flushed ------------------------
@@ -530,7 +547,7 @@ def main():
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra_multi)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()

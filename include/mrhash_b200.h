@@ -114,6 +114,16 @@ int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* norma
 
 /* GeoWrapper::compute (geowrapper.cpp:118-148) */
 int mrh_compute(mrh_map* m);
+/* Sharded maps (shard_world > 1) only. Every n_frames_invalidate_voxels-th frame the reference decrements
+ * the weight of the front-most voxel of each pixel (starveVoxelsKernel, voxel_data_structures.cu:1597-1671),
+ * found with a per-pixel atomicMin z-buffer; a shard sees only its own voxels, so on those frames
+ * mrh_compute_begin stops after the z-buffer pass and sets *needs_zbuf_reduce: the caller min-reduces
+ * the buffer (mrh_get_zbuf: int64 cells, device memory) over all ranks - the one collective of the
+ * integration path - and calls mrh_compute_end. On all other frames begin runs the whole frame.
+ * mrh_compute == begin + end without the reduction. */
+int mrh_compute_begin(mrh_map* m, int* needs_zbuf_reduce);
+int mrh_compute_end(mrh_map* m);
+int mrh_get_zbuf(mrh_map* m, void** d_zbuf, size_t* n_cells);
 /* wait for all queued work of this handle */
 int mrh_synchronize(mrh_map* m);
 

@@ -87,6 +87,9 @@ SIGNATURES = {
     "mrh_set_rgb_device": ([_vp, _vp, _i, _i], _i),
     "mrh_set_points": ([_vp, _vp, C.c_size_t, _vp], _i),
     "mrh_compute": ([_vp], _i),
+    "mrh_compute_begin": ([_vp, _P(_i)], _i),
+    "mrh_compute_end": ([_vp], _i),
+    "mrh_get_zbuf": ([_vp, _P(_vp), _P(C.c_size_t)], _i),
     "mrh_synchronize": ([_vp], _i),
     "mrh_stream_all_out": ([_vp], _i),
     "mrh_store_append": ([_vp, _vp, _vp, C.c_size_t], _i),

@@ -154,8 +154,10 @@ static void refresh_map_params(mrh_map* m) {
   if (p.shard_world > 1) {
     d.shard_lo = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) p.shard_rank / (uint64_t) p.shard_world);
     d.shard_hi = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) (p.shard_rank + 1) / (uint64_t) p.shard_world);
+    d.shard_tag = (uint32_t) p.shard_rank << 28;
   } else {
     d.shard_lo = 0, d.shard_hi = d.num_buckets;
+    d.shard_tag = 0;
   }
 }
 
@@ -451,8 +453,7 @@ int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* norma
   return 0;
 }
 
-int mrh_compute(mrh_map* m) {
-  GUARD(m);
+static int compute_frame(mrh_map* m) {
   const bool rgbd = m->depth_ptr && m->rgb_ptr;
   if (rgbd) {
     if (m->depth_rows != (int) m->cam.rows || m->depth_cols != (int) m->cam.cols || m->rgb_rows != m->depth_rows || m->rgb_cols != m->depth_cols)
@@ -491,6 +492,40 @@ int mrh_compute(mrh_map* m) {
 int mrh_synchronize(mrh_map* m) {
   GUARD(m);
   CK(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int mrh_compute(mrh_map* m) {
+  GUARD(m);
+  if (m->pending_gc)
+    return fail("mrh_compute: the previous frame is waiting for mrh_compute_end");
+  m->split_zbuf = false;
+  return compute_frame(m);
+}
+
+int mrh_compute_begin(mrh_map* m, int* needs_zbuf_reduce) {
+  GUARD(m);
+  if (!needs_zbuf_reduce)
+    return fail("null argument");
+  if (m->pending_gc)
+    return fail("mrh_compute_begin: the previous frame is waiting for mrh_compute_end");
+  m->split_zbuf = m->p.shard_world > 1;
+  const int rc  = compute_frame(m);
+  m->split_zbuf = false;
+  *needs_zbuf_reduce = m->pending_gc ? 1 : 0;
+  return rc;
+}
+
+int mrh_compute_end(mrh_map* m) {
+  GUARD(m);
+  return finish_gc_tail(m);
+}
+
+int mrh_get_zbuf(mrh_map* m, void** d_zbuf, size_t* n_cells) {
+  if (!m || !d_zbuf || !n_cells)
+    return fail("null argument");
+  *d_zbuf  = m->dev.zbuf;
+  *n_cells = (size_t) m->cam.rows * m->cam.cols;
   return 0;
 }
 

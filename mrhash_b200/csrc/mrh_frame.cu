@@ -72,28 +72,47 @@ namespace {
   }
 
   // GC tail when the fused kernel cannot be used (voxel_data_structures.cpp:137-145:
-  // [starve], identify, free)
+  // [starve], identify, free). On a sharded map the z-buffer of a starve frame holds only this rank's
+  // voxels; with split_zbuf the frame pauses after the z-buffer pass so that the caller can min-reduce
+  // it over the ranks (the front-most voxel of a pixel is then the front-most of the WHOLE map, as in
+  // the unsharded run) and finish_gc_tail resumes.
+  int gc_tail_finish(mrh_map* m, const FrameDev& f, bool starve, bool var) {
+    const MapDev& d    = m->dev;
+    cudaStream_t s     = m->stream;
+    const int grid_blocks = m->num_sms * 8, grid_list = m->num_sms * 4;
+    if (starve) {
+      k_starve<1><<<grid_blocks, 128, 0, s>>>(d, f, m->cam);
+      m->launches += 1;
+    }
+    k_identify<<<grid_blocks, 128, 0, s>>>(d);
+    k_gc_free<<<grid_blocks, 128, 0, s>>>(d, f);
+    m->launches += 2;
+    if (var) {
+      k_gc_low<<<grid_list, 128, 0, s>>>(d, f);
+      m->launches += 1;
+    }
+    CKL();
+    return 0;
+  }
+
   int gc_tail(FrameCtx& c, const FrameDev& f) {
     mrh_map* m         = c.m;
     const MapDev& d    = m->dev;
     const CameraDev& k = m->cam;
     cudaStream_t s     = m->stream;
     if (c.starve) {
-      if (cudaMemsetAsync(d.zbuf, 0xFF, sizeof(unsigned long long) * k.rows * k.cols, s) != cudaSuccess)
+      // 0x7F bytes: above every packed (depth, id) value and still positive as int64 (NCCL MIN)
+      if (cudaMemsetAsync(d.zbuf, 0x7F, sizeof(unsigned long long) * k.rows * k.cols, s) != cudaSuccess)
         return fail("memset zbuf failed");
       k_starve<0><<<c.grid_blocks, 128, 0, s>>>(d, f, k);
-      k_starve<1><<<c.grid_blocks, 128, 0, s>>>(d, f, k);
-      m->launches += 2;
-    }
-    k_identify<<<c.grid_blocks, 128, 0, s>>>(d);
-    k_gc_free<<<c.grid_blocks, 128, 0, s>>>(d, f);
-    m->launches += 2;
-    if (c.var) {
-      k_gc_low<<<c.grid_list, 128, 0, s>>>(d, f);
       m->launches += 1;
+      CKL();
+      if (m->split_zbuf) {
+        m->pending_gc = true, m->pending_f = f, m->pending_var = c.var;
+        return 0;
+      }
     }
-    CKL();
-    return 0;
+    return gc_tail_finish(m, f, c.starve, c.var);
   }
 
   // checkVarSDF + reallocBlocks + flatAndReduceHashTable (voxel_data_structures.cpp:99-103);
@@ -123,6 +142,13 @@ namespace {
   }
 
 } // namespace
+
+int finish_gc_tail(mrh_map* m) {
+  if (!m->pending_gc)
+    return 0;
+  m->pending_gc = false;
+  return gc_tail_finish(m, m->pending_f, true, m->pending_var);
+}
 
 // used by stream-in: make room for n_low resolution-1 blocks
 int carve_low_blocks(mrh_map* m, uint32_t n_low) {

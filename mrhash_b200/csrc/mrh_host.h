@@ -81,6 +81,11 @@ struct mrh_map {
   size_t n_points = 0;
   float* d_points = nullptr;
 
+  // sharded starve frames: the frame stops after the z-buffer pass (mrh_compute_begin) so that the
+  // caller can min-reduce the z-buffer over the ranks, and resumes in mrh_compute_end
+  bool split_zbuf = false, pending_gc = false, pending_var = false;
+  mrh::FrameDev pending_f{};
+
   uint32_t frame_index = 0; // num_integrated_frames_ (voxel_data_structures.cpp:106)
   uint32_t live_cur    = 0;
   bool counters_clean  = true; // live_count[live_cur ^ 1] and vis_count are already zero (fast RGB-D path precondition)
@@ -129,5 +134,6 @@ namespace mrh {
   int weld_on_device(mrh_map* m, const float* d_soup, size_t n_tri, double eps);
   int integrate_rgbd(mrh_map* m);
   int integrate_points(mrh_map* m);
+  int finish_gc_tail(mrh_map* m);
   FrameDev make_frame(const mrh_map* m);
 } // namespace mrh

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(128) k_starve(MapDev m, FrameDev f, CameraDev 
       if (!project_point(cam, pc, row, col))
         continue;
       // pack(unique_tid, depth) (:1583-1585, :1629-1641)
-      const unsigned long long packed = ((unsigned long long) __float_as_uint(d) << 32) + (unsigned long long) (uint32_t) (kBlockVoxels * bi + i);
+      const unsigned long long packed = ((unsigned long long) __float_as_uint(d) << 32) + (unsigned long long) (m.shard_tag | (uint32_t) (kBlockVoxels * bi + i));
       unsigned long long* cell = m.zbuf + (size_t) row * cam.cols + col;
       if (PASS == 0) {
         atomicMin(cell, packed);

@@ -101,6 +101,7 @@ struct MapDev {
   uint32_t num_buckets, capacity, num_blocks;
   uint32_t bucket_magic; // floor(2^32 / num_buckets): block_hash_fast needs no integer division
   uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
+  uint32_t shard_tag;          // shard_rank << 28: makes the starve z-buffer ids unique across ranks
   unsigned long long* keys;
   uint32_t* vals;
   uint32_t* heap;

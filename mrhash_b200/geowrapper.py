@@ -79,6 +79,7 @@ class GeoWrapper:
         h = C.c_void_p()
         check(self._lib.mrh_create(C.byref(p), C.byref(h)))
         self._h = h
+        self._shard_world = int(shard_world)
         self._device = int(self._get("Device"))
         self._points = np.zeros((0, 3), np.float32)
         self._normals = np.zeros((0, 3), np.float32)
@@ -265,6 +266,28 @@ class GeoWrapper:
     def compute(self):
         check(self._lib.mrh_compute(self._h))
 
+    def computeBegin(self):
+        """Sharded maps: compute() up to the point where a starve frame needs the z-buffer min-reduced
+        over the ranks. Returns True when that reduction is due before computeEnd()."""
+        need = C.c_int()
+        check(self._lib.mrh_compute_begin(self._h, C.byref(need)))
+        return bool(need.value)
+
+    def computeEnd(self):
+        check(self._lib.mrh_compute_end(self._h))
+
+    def zbufTensor(self):
+        """The starve z-buffer as a torch int64 CUDA tensor (a view of the library's memory)."""
+        import torch
+
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check(self._lib.mrh_get_zbuf(self._h, C.byref(ptr), C.byref(n)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<i8", "data": (ptr.value, False), "version": 2}
+
+        return torch.as_tensor(_View(), device=torch.device("cuda", self._device))
+
     def synchronize(self):
         check(self._lib.mrh_synchronize(self._h))
 
@@ -370,6 +393,10 @@ class GeoWrapper:
 
     def setShard(self, shard_rank, shard_world):
         check(self._lib.mrh_set_shard(self._h, int(shard_rank), int(shard_world)))
+        self._shard_world = int(shard_world)
+
+    def shardWorld(self):
+        return self._shard_world
 
     # ---- sharded meshing: boundary exchange (include/mrhash_b200.h, csrc/mrh_halo.cu). The tensors
     # are torch CUDA tensors on this handle's device; torch is only the buffer / NCCL plumbing. ----

@@ -54,6 +54,31 @@ def broadcast_frame(depth, rgb, pose, src=0, group=None):
     dist.broadcast(rgb, src, group=group)
 
 
+def compute_sharded(geo, group=None):
+    """compute() of one rank of a sharded map. Integration itself needs no exchange; the exception is
+    the starve frame (every n_frames_invalidate_voxels-th): the per-pixel front-most voxel has to be the
+    front-most of the WHOLE map, so the z-buffer (8 bytes per pixel) is min-reduced over the ranks
+    between the two starve passes - one NCCL all-reduce every n-th frame, ordered with events only."""
+    import torch
+    import torch.distributed as dist
+
+    if not geo.computeBegin():
+        geo.computeEnd()
+        return False
+    zb = geo.zbufTensor()
+    lib_stream = torch.cuda.ExternalStream(geo.cudaStream(), device=zb.device)
+    ev = torch.cuda.Event()
+    ev.record(lib_stream)
+    cur = torch.cuda.current_stream(zb.device)
+    cur.wait_event(ev)
+    dist.all_reduce(zb, op=dist.ReduceOp.MIN, group=group)
+    ev2 = torch.cuda.Event()
+    ev2.record(cur)
+    lib_stream.wait_event(ev2)
+    geo.computeEnd()
+    return True
+
+
 def gather_blocks(entries, voxels, dst=0, group=None, device="cpu"):
     """Gather every rank's (entries [n,5] int32, voxels [n,512] VOXEL_DTYPE) on `dst`.
     Returns the merged, key-sorted (entries, voxels) on dst and (None, None) elsewhere."""
