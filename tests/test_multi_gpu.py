@@ -321,9 +321,11 @@ def test_starve_frames_min_reduce_the_zbuffer_across_shards():
     rep, n_reduced = run(True)
     print(f"[starve, z-buffer reduced x{n_reduced}]", rep)
     assert n_reduced == 2  # frames 3 and 6
-    assert rep["only_a"] == 0 and rep["only_b"] == 0 and rep["sdf_mismatch"] == 0
-    # equal-depth ties are broken by list position (racy in the reference as well)
+    assert rep["only_a"] == 0 and rep["only_b"] == 0
+    # equal-depth ties are broken by list position (racy in the reference as well); a
+    # voxel whose weight differs by that one unit then fuses the next frame slightly differently
     assert rep["weight_mismatch"] <= 1e-4 * rep["voxels_compared"]
+    assert rep["sdf_mismatch"] <= rep["weight_mismatch"] and rep["sum_squared_mismatch"] <= rep["weight_mismatch"]
     rep_no, _ = run(False)
     print("[starve, no reduction]", {k: rep_no[k] for k in ("only_a", "only_b", "weight_mismatch")})
     assert rep_no["weight_mismatch"] > 10 * max(1, rep["weight_mismatch"])  # the reduction is what makes it right

@@ -22,7 +22,21 @@ for k in range(n_frames):
     d, c = synth.render_rgbd_torch(R, t, w, h, device="cuda")
     torch.cuda.synchronize()
     for g in shards + [whole]:
-        g.setCurrPose(t, q); g.setDepthImageDevice(d.data_ptr(), h, w); g.setRGBImageDevice(c.data_ptr(), h, w); g.compute(); g.synchronize()
+        g.setCurrPose(t, q); g.setDepthImageDevice(d.data_ptr(), h, w); g.setRGBImageDevice(c.data_ptr(), h, w)
+    whole.compute(); whole.synchronize()
+    need = [g.computeBegin() for g in shards]
+    if need[0]:  # starve frame: what sharding.compute_sharded does with an NCCL all-reduce(MIN)
+        for g in shards:
+            g.synchronize()
+        zs = [g.zbufTensor() for g in shards]
+        zmin = zs[0].clone()
+        for z in zs[1:]:
+            zmin = torch.minimum(zmin, z)
+        for z in zs:
+            z.copy_(zmin)
+        torch.cuda.synchronize()
+    for g in shards:
+        g.computeEnd(); g.synchronize()
 for r, g in enumerate(shards):
     st0 = g.getStats()
     e, _ = g.dumpState()
