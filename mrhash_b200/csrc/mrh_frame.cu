@@ -31,6 +31,16 @@ FrameDev make_frame(const mrh_map* m) {
       f.R[i * 3 + j] = m->pose[i * 4 + j];
     f.t[i] = m->pose[i * 4 + 3];
   }
+  // CUDAMatSE3::inverse() (cuda_algebra.cuh:137-143) as pose_finish (mrh_math.cuh) evaluates it on the
+  // device: R^T, then -(R^T t) with row_dot's contraction fma(c, z, fma(a, x, b * y)). fmaf is
+  // correctly rounded on the host too, so the bits are the same.
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      f.Ri[j * 3 + i] = f.R[i * 3 + j];
+  for (int i = 0; i < 3; ++i) {
+    volatile float by = f.Ri[i * 3 + 1] * f.t[1];
+    f.ti[i]           = -std::fmaf(f.Ri[i * 3 + 2], f.t[2], std::fmaf(f.Ri[i * 3 + 0], f.t[0], by));
+  }
   f.frame_index = m->frame_index;
   f.live_cur    = m->live_cur;
   f.pad[0] = f.pad[1] = 0;
@@ -178,11 +188,11 @@ int integrate_rgbd(mrh_map* m) {
       k_zero_frame_counters<<<1, 1, 0, s>>>(d, f.live_cur ^ 1u);
       m->launches += 1;
     }
-    const uint32_t tiles_x = (k.cols + 31) / 32, tiles_y = (k.rows + 7) / 8;
+    const uint32_t tiles_x = (k.cols + 31) / 32, tiles_y = (k.rows + kFrontWarps - 1) / kFrontWarps;
     const uint32_t n_vis_ctas = (uint32_t) m->num_sms;
     const int rearm           = c.starve ? 0 : 1;
     mark(0);
-    k_front<<<tiles_x * tiles_y + n_vis_ctas, 256, 0, s>>>(d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
+    k_front<<<tiles_x * tiles_y + n_vis_ctas, kFrontThreads, 0, s>>>(d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
     CKL();
     mark(1);
     if (m->rgb_ready)

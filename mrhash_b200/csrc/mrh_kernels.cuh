@@ -181,15 +181,12 @@ __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uin
 // CTA has read vis_count by then), so a frame needs no reset kernel.
 template <bool FUSE_GC>
 __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
-  __shared__ PoseDev pose;
   __shared__ float s_min[4];
   __shared__ uint32_t s_max[4];
   __shared__ uint32_t s_upd[4];
   __shared__ int s_delete;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0)
-    load_pose(f, pose);
-  __syncthreads();
+  const PoseDev& pose  = frame_pose(f);
   const uint32_t n_vis = m.ctr->vis_count;
   const int lx0 = (tid & 1) * 4, ly = (tid >> 1) & 7, lz = tid >> 4;
   const float half_size = fmul(m.voxel_size, 0.5f);
@@ -198,6 +195,14 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
     const VisEntry e = m.vis[bi];
     if (e.val & 0x80000000u)
       continue; // resolution-1 blocks are fused by k_integrate_lowres
+    uint8_t* base = m.pool + (size_t) e.val * kBlockBytes;
+    if (e.maybe_in_image && (tid & 7) == 0) {
+      // the three planes are read after the projection pass: start moving their lines (one per 8
+      // threads) towards L2 now, the projection and the depth gathers hide the DRAM latency
+      prefetch_l2(base + 16 * tid);
+      prefetch_l2(base + kPlaneBytes + 16 * tid);
+      prefetch_l2(base + 2 * kPlaneBytes + 16 * tid);
+    }
     // ---- pass 1: projection + depth test, registers only ----
     float sdf_new[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t pix[4]  = {0u, 0u, 0u, 0u};
@@ -228,7 +233,6 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
     const int any = e.maybe_in_image ? __syncthreads_or((int) ok) : 0;
     float min_abs  = 3.40282346638528859812e+38f;
     uint32_t max_w = 0, n_upd = 0;
-    uint8_t* base  = m.pool + (size_t) e.val * kBlockBytes;
     float4 sdf4, ss4;
     uint4 cw4;
     if (any) {

@@ -222,8 +222,8 @@ __device__ __forceinline__ uint32_t block_hash(i3 b, uint32_t num_buckets) {
 // Amanatides-Woo DDA state shared by the block walk (allocBlocksKernel :782-857,
 // allocBlocks3DKernel :963-1033) and the voxel walk (integrate3DKernel :1259-1378).
 struct DDA {
-  i3 cur, bound;
-  f3 t_max, t_delta, step;
+  i3 cur, bound, istep;
+  f3 t_max, t_delta;
   __device__ __forceinline__ void init(f3 p0, f3 p1, float size, const float* ext, bool block_level) {
     const f3 dir = normalize3({fsub(p1.x, p0.x), fsub(p1.y, p0.y), fsub(p1.z, p0.z)});
     i3 end;
@@ -234,16 +234,20 @@ struct DDA {
       cur = world_to_voxel(p0, size);
       end = world_to_voxel(p1, size);
     }
-    step            = {i2f(sign_i(dir.x)), i2f(sign_i(dir.y)), i2f(sign_i(dir.z))};
+    // The reference keeps the step as a float3 and advances with int(float(id) + step)
+    // (voxel_data_structures.cu:803,826-854): for |id| < 2^24 that is exactly id + sign, so the step
+    // lives here as an integer (coordinates beyond 2^24 cells are outside the key range anyway).
+    istep           = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
+    const f3 step   = {i2f(istep.x), i2f(istep.y), i2f(istep.z)};
     const float nh  = -fmul(0.5f, size);
     const int scale = block_level ? kBlockSide : 1;
     const float cell = block_level ? fmul(8.f, size) : size; // (step*8)*size == step*(8*size): step is 0/+-1
-    const float bx = ffma(i2f((cur.x + f2i(__saturatef(step.x))) * scale), size, nh);
-    const float by = ffma(i2f((cur.y + f2i(__saturatef(step.y))) * scale), size, nh);
-    const float bz = ffma(i2f((cur.z + f2i(__saturatef(step.z))) * scale), size, nh);
+    const float bx = ffma(i2f((cur.x + max(istep.x, 0)) * scale), size, nh); // clamp(step, 0, 1)
+    const float by = ffma(i2f((cur.y + max(istep.y, 0)) * scale), size, nh);
+    const float bz = ffma(i2f((cur.z + max(istep.z, 0)) * scale), size, nh);
     t_max   = {fdiv(fsub(bx, p0.x), dir.x), fdiv(fsub(by, p0.y), dir.y), fdiv(fsub(bz, p0.z), dir.z)};
     t_delta = {fdiv(fmul(step.x, cell), dir.x), fdiv(fmul(step.y, cell), dir.y), fdiv(fmul(step.z, cell), dir.z)};
-    bound   = {f2i(fadd(i2f(end.x), step.x)), f2i(fadd(i2f(end.y), step.y)), f2i(fadd(i2f(end.z), step.z))};
+    bound   = {end.x + istep.x, end.y + istep.y, end.z + istep.z};
     const float big = 3.40282346638528859812e+38f;
     if (fabsf(dir.x) < 1e-6f || fabsf(fsub(bx, dir.x)) < 1e-6f)
       t_max.x = big, t_delta.x = big;
@@ -255,17 +259,17 @@ struct DDA {
   // returns false when the walk leaves the segment (the reference `return`s)
   __device__ __forceinline__ bool advance() {
     if (t_max.x < t_max.y && t_max.x < t_max.z) {
-      cur.x = f2i(fadd(i2f(cur.x), step.x));
+      cur.x += istep.x;
       if (cur.x == bound.x)
         return false;
       t_max.x = fadd(t_max.x, t_delta.x);
     } else if (t_max.z < t_max.y) {
-      cur.z = f2i(fadd(i2f(cur.z), step.z));
+      cur.z += istep.z;
       if (cur.z == bound.z)
         return false;
       t_max.z = fadd(t_max.z, t_delta.z);
     } else {
-      cur.y = f2i(fadd(i2f(cur.y), step.y));
+      cur.y += istep.y;
       if (cur.y == bound.y)
         return false;
       t_max.y = fadd(t_max.y, t_delta.y);

@@ -84,6 +84,8 @@ struct GatherRecord {
 struct FrameDev {
   float R[9];
   float t[3];
+  float Ri[9]; // inverse pose, filled on the host by make_frame with pose_finish's exact arithmetic:
+  float ti[3]; // the first 24 floats have the layout of PoseDev (frame_pose)
   uint32_t frame_index;
   uint32_t live_cur; // which live list is the input of this frame
   uint32_t pad[2];
@@ -116,6 +118,15 @@ struct MapDev {
   unsigned long long* zbuf;
   Counters* ctr;
 };
+
+// The pose straight out of the kernel parameters (constant bank): no shared-memory staging, no barrier.
+static_assert(sizeof(PoseDev) == 24 * sizeof(float), "PoseDev layout");
+__device__ __forceinline__ const PoseDev& frame_pose(const FrameDev& f) {
+  return *reinterpret_cast<const PoseDev*>(f.R);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __device__ __forceinline__ bool key_in_range(i3 b) {
   return (unsigned) (b.x + kCoordBias) < (2u * kCoordBias) && (unsigned) (b.y + kCoordBias) < (2u * kCoordBias) &&
