@@ -124,6 +124,13 @@ int mrh_compute(mrh_map* m);
 int mrh_compute_begin(mrh_map* m, int* needs_zbuf_reduce);
 int mrh_compute_end(mrh_map* m);
 int mrh_get_zbuf(mrh_map* m, void** d_zbuf, size_t* n_cells);
+/* Streamer::stream (streamer.cpp:337-355): blocks whose origin is at least `radius` away from `centre`
+ * leave the device for the host store, stored blocks whose 1 m chunk lies inside the sphere come back.
+ * mrh_compute calls it by itself with (camera position, max_depth) when no more than
+ * StreamThreshold (field, default 0.15 = params.h:28; 0 = never) of the pool is free, as
+ * GeoWrapper::compute does (geowrapper.cpp:137-138); the free count it looks at is the one of the last
+ * completed frame. Fields StreamEvents, LastStreamOutBlocks, LastStreamInBlocks, StreamDuplicates report it. */
+int mrh_stream(mrh_map* m, const float centre[3], float radius);
 /* wait for all queued work of this handle */
 int mrh_synchronize(mrh_map* m);
 
@@ -137,6 +144,8 @@ int mrh_store_append(mrh_map* m, const mrh_dump_entry* entries, const void* voxe
 int mrh_set_shard(mrh_map* m, int shard_rank, int shard_world);
 /* number of blocks currently held by the host store (the reference's Streamer::grid_) */
 int mrh_store_size(mrh_map* m, size_t* n_blocks);
+/* test / tooling: copy of the host store in store order (same layouts as mrh_dump_state; duplicates of a key, if any, included) */
+int mrh_store_read(mrh_map* m, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out);
 /* GeoWrapper::extractMesh (geowrapper.cpp:150-230): marching cubes + host weld + ASCII PLY (path may be NULL: no file) */
 int mrh_extract_mesh(mrh_map* m, const char* path_or_null);
 /* same; force_generic != 0 sends every block through the per-read hash sampler (test / validation of the shared-memory path) */

@@ -90,11 +90,13 @@ SIGNATURES = {
     "mrh_compute_begin": ([_vp, _P(_i)], _i),
     "mrh_compute_end": ([_vp], _i),
     "mrh_get_zbuf": ([_vp, _P(_vp), _P(C.c_size_t)], _i),
+    "mrh_stream": ([_vp, _fp, _f], _i),
     "mrh_synchronize": ([_vp], _i),
     "mrh_stream_all_out": ([_vp], _i),
     "mrh_store_append": ([_vp, _vp, _vp, C.c_size_t], _i),
     "mrh_set_shard": ([_vp, _i, _i], _i),
     "mrh_store_size": ([_vp, _P(C.c_size_t)], _i),
+    "mrh_store_read": ([_vp, _vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),
     "mrh_extract_mesh": ([_vp, C.c_char_p], _i),
     "mrh_extract_mesh_ex": ([_vp, C.c_char_p, _i], _i),
     "mrh_get_mesh": ([_vp, _P(_P(C.c_double)), _P(_P(C.c_int32)), _P(_P(C.c_double)), _P(C.c_size_t), _P(C.c_size_t)], _i),

@@ -124,6 +124,9 @@ static void free_map(mrh_map* m) {
   cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
+  cudaFreeHost(m->h_heap_probe);
+  if (m->ev_probe)
+    cudaEventDestroy(m->ev_probe);
   for (int i = 0; i < 8; ++i)
     if (m->ev_k[i])
       cudaEventDestroy(m->ev_k[i]);
@@ -266,6 +269,8 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
       CK(cudaEventCreateWithFlags(&in->consumed[i], cudaEventDisableTiming));
     }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
+  CK(cudaMallocHost(&m->h_heap_probe, sizeof(int)));
+  CK(cudaEventCreateWithFlags(&m->ev_probe, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i)
     CK(cudaEventCreate(&m->ev_k[i]));
   cudaDeviceProp prop;
@@ -460,6 +465,16 @@ static int compute_frame(mrh_map* m) {
       return fail("mrh_compute: depth %dx%d / rgb %dx%d do not match the camera %ux%u", m->depth_rows, m->depth_cols, m->rgb_rows, m->rgb_cols, m->cam.rows, m->cam.cols);
   }
   refresh_map_params(m);
+  // GeoWrapper::compute (geowrapper.cpp:137-138): page when the pool runs low. The free count is the
+  // one probed at the end of the last frame whose probe has arrived (no device wait here).
+  if (m->probe_valid && m->stream_threshold > 0.f && cudaEventQuery(m->ev_probe) == cudaSuccess) {
+    m->probe_valid = false;
+    if ((double) (*m->h_heap_probe + 1) <= (double) m->stream_threshold * (double) m->num_sdf_blocks) {
+      const float centre[3] = {m->pose[3], m->pose[7], m->pose[11]};
+      if (stream_radius(m, centre, m->cam.max_depth))
+        return 1;
+    }
+  }
   Ingest* used[3] = {rgbd ? &m->in_depth : nullptr, rgbd ? &m->in_rgb : nullptr, m->n_points ? &m->in_points : nullptr};
   // the ray walk needs the depth image (or the points) only: the colour transfer overlaps it and is
   // waited for in front of the first fusion kernel (integrate_rgbd)
@@ -477,6 +492,11 @@ static int compute_frame(mrh_map* m) {
   if (m->n_points && integrate_points(m))
     return 1;
   CK(cudaEventRecord(m->ev1, m->stream));
+  if (m->stream_threshold > 0.f && !m->pending_gc) {
+    CK(cudaMemcpyAsync(m->h_heap_probe, &m->dev.ctr->heap_counter, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev_probe, m->stream));
+    m->probe_valid = true;
+  }
   for (Ingest* in : used)
     if (in && in->active)
       CK(cudaEventRecord(in->consumed[in->which], m->stream));
@@ -565,6 +585,11 @@ int mrh_get_field(mrh_map* m, const char* name, double* out) {
   else if (n == "LastMeshMergeMs") *out = m->mesh_ms_merge;
   else if (n == "LastMeshPlyMs") *out = m->mesh_ms_ply;
   else if (n == "Device") *out = m->device;
+  else if (n == "StreamThreshold") *out = m->stream_threshold;
+  else if (n == "StreamEvents") *out = (double) m->stream_events;
+  else if (n == "LastStreamOutBlocks") *out = (double) m->last_stream_out;
+  else if (n == "LastStreamInBlocks") *out = (double) m->last_stream_in;
+  else if (n == "StreamDuplicates") *out = (double) m->stream_duplicates;
   else if (n == "LowResolutionBlocks") *out = (double) (m->p.sdf_var_threshold > 0.f || m->h_ctr->low_live > 0);
   else
     return fail("mrh_get_field: unknown field '%s'", name);
@@ -591,6 +616,7 @@ int mrh_set_field(mrh_map* m, const char* name, double v) {
   else if (n == "SDFVarThreshold") p.sdf_var_threshold = (float) v;
   else if (n == "VerticesMergingThreshold") p.vertices_merging_threshold = (float) v;
   else if (n == "MarchingCubesThreshold") p.marching_cubes_threshold = (float) v;
+  else if (n == "StreamThreshold") m->stream_threshold = (float) v; // params.h:28, 0 switches paging off
   else
     return fail("mrh_set_field: unknown field '%s'", name);
   refresh_map_params(m);

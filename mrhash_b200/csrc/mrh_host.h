@@ -120,6 +120,13 @@ struct mrh_map {
   bool halo_active       = false;
   uint32_t halo_owned    = 0;
   uint16_t* d_shell_idx  = nullptr;
+  // radius paging (Streamer::stream): trigger when free pool blocks <= stream_threshold * num_sdf_blocks
+  // (params.h:28); the free count is probed asynchronously at the end of every frame
+  float stream_threshold  = 0.15f;
+  int* h_heap_probe       = nullptr; // pinned
+  cudaEvent_t ev_probe    = nullptr;
+  bool probe_valid        = false;
+  uint64_t stream_events = 0, last_stream_out = 0, last_stream_in = 0, stream_duplicates = 0;
   mrh::HostStore store;
   mrh::HostMesh mesh;
   // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel, device weld + D2H of the mesh, PLY
@@ -128,7 +135,12 @@ struct mrh_map {
 
 namespace mrh {
   int reset_map(mrh_map* m);
-  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels);
+  // far_centre != nullptr: only blocks at least far_radius away, which also leave the device map
+  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels, const float* far_centre = nullptr, float far_radius = 0.f);
+  // Streamer::stream (streamer.cpp:337-355): page far blocks out, page the host blocks around centre in
+  int stream_radius(mrh_map* m, const float centre[3], float radius);
+  // chunk test of Streamer::isChunkInSphere for the record's chunk (streamer.cuh:346-352)
+  bool record_in_sphere(const mrh_map* m, const GatherRecord& r, const float centre[3], float radius);
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
   int carve_low_blocks(mrh_map* m, uint32_t n_low);
   int weld_on_device(mrh_map* m, const float* d_soup, size_t n_tri, double eps);

@@ -194,7 +194,6 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
   const float ext   = (float) m->p.voxel_extents_scale;
   const float radius = 10.f * m->cam.max_depth; // radius_scale_chunk (params.h:35)
   const int radiusi  = (int) radius;
-  const float chunk_radius = 0.5f * ext * std::sqrt(3.f); // streamer.cpp:15
   // computeBounds (streamer.cuh:357-368). The reference's grid keeps the keys of emptied chunks, so
   // the bounds are those of everything that was ever streamed out; here: of the current store.
   int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
@@ -218,11 +217,7 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
           std::vector<uint8_t> inside(st.recs.size());
           size_t n_in = 0;
           for (size_t i = 0; i < st.recs.size(); ++i) {
-            int c[3];
-            block_chunk(st.recs[i], size, ext, c);
-            const float d[3] = {(float) c[0] * ext - centre[0], (float) c[1] * ext - centre[1], (float) c[2] * ext - centre[2]};
-            const float l    = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-            inside[i]        = l <= std::fabs(radius - chunk_radius);
+            inside[i] = record_in_sphere(m, st.recs[i], centre, radius);
             n_in += inside[i];
           }
           if (n_in == st.recs.size()) {

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <numeric>
 #include <thread>
+#include <unordered_map>
 
 #include "mrh_host.h"
 #include "mrh_table.cuh"
@@ -29,7 +30,14 @@ namespace mrh {
 // serializeData / the parity dump (replaces the Streamer's integrateFromGlobalHashPass1/2,
 // streamer.cu:77-187: no per-thread serial prefix sums).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_cur, GatherRecord* records, uint32_t* voxels_aos, uint32_t* out_count, uint32_t first, uint32_t max_out) {
+// far_release: radius paging (integrateFromGlobalHashPass1Kernel, streamer.cu:11-59): only blocks whose
+// origin is at least `radius` away from `centre` are gathered, and each one leaves the map (key
+// tombstoned, pool storage zeroed and pushed back on its heap, live entry invalidated).
+struct FarFilter {
+  float cx, cy, cz, radius;
+  int far_release;
+};
+__global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_cur, GatherRecord* records, uint32_t* voxels_aos, uint32_t* out_count, uint32_t first, uint32_t max_out, FarFilter ff) {
   __shared__ uint32_t s_out;
   const int tid    = threadIdx.x;
   const uint32_t n = min(m.ctr->live_count[live_cur], first + max_out);
@@ -39,6 +47,15 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
       continue;
     const unsigned long long key = le.key;
     const uint32_t val           = le.val;
+    if (ff.far_release) {
+      // SDFBlockToWorldPoint (voxel_hash_utils.cuh:163-165) and length(a, b) (cuda_math.cuh:1062-1065)
+      const i3 kb  = unpack_key(key);
+      const float dx = fsub(fmul(i2f(kb.x * kBlockSide), m.voxel_size), ff.cx), dy = fsub(fmul(i2f(kb.y * kBlockSide), m.voxel_size), ff.cy),
+                  dz = fsub(fmul(i2f(kb.z * kBlockSide), m.voxel_size), ff.cz);
+      const float d  = __fsqrt_rn(ffma(dz, dz, ffma(dx, dx, fmul(dy, dy))));
+      if (!(d >= ff.radius))
+        continue;
+    }
     if (tid == 0)
       s_out = atomicAdd(out_count, 1u);
     __syncthreads();
@@ -76,6 +93,33 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
         dst[v * 3 + 0] = a, dst[v * 3 + 1] = b2, dst[v * 3 + 2] = c;
       }
     }
+    if (ff.far_release) {
+      __syncthreads(); // every thread has read its voxels
+      if (!(val >> 31)) {
+        uint8_t* base  = m.pool + (size_t) val * kBlockBytes;
+        const float4 z = {0.f, 0.f, 0.f, 0.f};
+        reinterpret_cast<float4*>(base)[tid]                   = z;
+        reinterpret_cast<float4*>(base + kPlaneBytes)[tid]     = z;
+        reinterpret_cast<float4*>(base + 2 * kPlaneBytes)[tid] = z;
+      } else {
+        uint8_t* base = m.pool + (size_t) (val & 0x7FFFFFFFu) * 768u;
+        for (int w = tid; w < 192; w += 128)
+          reinterpret_cast<uint32_t*>(base)[w] = 0u;
+      }
+      if (tid == 0) {
+        atomicExch(m.keys + le.slot, kTomb);
+        if (val >> 31) {
+          const int addr       = atomicAdd(&m.ctr->heap_low_counter, 1);
+          m.heap_low[addr + 1] = val & 0x7FFFFFFFu;
+          atomicAdd(&m.ctr->low_live, (unsigned long long) -1ll);
+        } else {
+          const int addr   = atomicAdd(&m.ctr->heap_counter, 1);
+          m.heap[addr + 1] = val;
+          m.stats[val]     = {3.40282346638528859812e+38f, 0u};
+        }
+        m.live[live_cur][i].slot = kInvalid;
+      }
+    }
   }
 }
 
@@ -95,8 +139,27 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
           s_val = v;
       }
       __syncthreads();
-      const uint32_t val = s_val;
+      uint32_t val = s_val;
       __syncthreads();
+      // The key is live already: the block was paged out, and allocated again before it came back
+      // (the reference ends up with two entries of one key there, tests/test_streamer.cu:40-117 bounds
+      // their ratio). Here the stored observations are fused into the live block with the running
+      // weighted mean of combineVoxel (voxel_hash_utils.cuh:169-181), so nothing is lost or doubled.
+      bool merge = false;
+      if (val == kInvalid && r.resolution == 0) {
+        if (tid == 0) {
+          const int sl = table_find(m, {r.x, r.y, r.z});
+          s_val        = sl >= 0 ? m.vals[sl] : kInvalid;
+          if (sl >= 0)
+            atomicAdd(&m.ctr->stream_merged, 1ull);
+        }
+        __syncthreads();
+        val = s_val;
+        __syncthreads();
+        merge = val != kInvalid && !(val >> 31);
+        if (!merge)
+          val = kInvalid;
+      }
       if (val == kInvalid)
         continue;
       const uint32_t* src = voxels_aos + (size_t) i * kBlockVoxels * 3;
@@ -109,11 +172,28 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
         uint32_t* cv = reinterpret_cast<uint32_t*>(&cw4);
         float min_abs  = 3.40282346638528859812e+38f;
         uint32_t max_w = 0;
+        if (merge) {
+          sdf4 = reinterpret_cast<const float4*>(base)[tid];
+          ss4  = reinterpret_cast<const float4*>(base + kPlaneBytes)[tid];
+          cw4  = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          sv[j] = __uint_as_float(src[(tid * 4 + j) * 3 + 0]);
-          qv[j] = __uint_as_float(src[(tid * 4 + j) * 3 + 1]);
-          cv[j] = src[(tid * 4 + j) * 3 + 2];
+          const float s1    = __uint_as_float(src[(tid * 4 + j) * 3 + 0]);
+          const float q1    = __uint_as_float(src[(tid * 4 + j) * 3 + 1]);
+          const uint32_t c1 = src[(tid * 4 + j) * 3 + 2];
+          const uint32_t w1 = c1 >> 24, w0 = merge ? cv[j] >> 24 : 0u;
+          if (!merge || w0 == 0) {
+            if (!merge || w1)
+              sv[j] = s1, qv[j] = q1, cv[j] = c1;
+          } else if (w1) {
+            const uint32_t c0 = cv[j];
+            sv[j]             = fdiv(ffma(s1, __uint2float_rn(w1), fmul(sv[j], __uint2float_rn(w0))), __uint2float_rn(w0 + w1));
+            const uint32_t rr = (uint32_t) f2i(fadd(ffma(__uint2float_rn(c1 & 0xFF), 0.5f, fmul(__uint2float_rn(c0 & 0xFF), 0.5f)), 0.5f)) & 0xFF;
+            const uint32_t gg = (uint32_t) f2i(fadd(ffma(__uint2float_rn((c1 >> 8) & 0xFF), 0.5f, fmul(__uint2float_rn((c0 >> 8) & 0xFF), 0.5f)), 0.5f)) & 0xFF;
+            const uint32_t bb = (uint32_t) f2i(fadd(ffma(__uint2float_rn((c1 >> 16) & 0xFF), 0.5f, fmul(__uint2float_rn((c0 >> 16) & 0xFF), 0.5f)), 0.5f)) & 0xFF;
+            cv[j]             = rr | (gg << 8) | (bb << 16) | (min(w0 + w1, (uint32_t) kWeightMax) << 24);
+          }
           if (cv[j] >> 24)
             min_abs = fminf(min_abs, fabsf(sv[j]));
           max_w = max(max_w, cv[j] >> 24);
@@ -145,7 +225,10 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   }
 
   // Gather every live block of the device map into host vectors (appended).
-  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels) {
+  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels, const float* far_centre, float far_radius) {
+    FarFilter ff{0.f, 0.f, 0.f, 0.f, 0};
+    if (far_centre)
+      ff = {far_centre[0], far_centre[1], far_centre[2], far_radius, 1};
     mrh_stats st;
     if (mrh_get_stats(m, &st))
       return 1;
@@ -167,7 +250,7 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     size_t done           = 0;
     for (uint32_t first = 0; first < n_list; first += (uint32_t) chunk) {
       CK(cudaMemsetAsync(d_count, 0, sizeof(uint32_t), m->stream));
-      k_gather_blocks<<<m->num_sms * 8, 128, 0, m->stream>>>(m->dev, m->live_cur, d_recs, d_vox, d_count, first, (uint32_t) chunk);
+      k_gather_blocks<<<m->num_sms * 8, 128, 0, m->stream>>>(m->dev, m->live_cur, d_recs, d_vox, d_count, first, (uint32_t) chunk, ff);
       m->launches++;
       uint32_t got = 0;
       CK(cudaMemcpyAsync(&got, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream));
@@ -186,15 +269,8 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     return 0;
   }
 
-  // Streamer::streamInToGPU (streamer.cpp:358-378) for a selection of host-store records.
-  int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
-    if (n == 0)
-      return 0;
-    uint32_t n_low = 0;
-    for (size_t i = 0; i < n; ++i)
-      n_low += recs[i].resolution != 0;
-    if (carve_low_blocks(m, n_low))
-      return 1;
+  // one pass: records with pairwise different keys
+  static int insert_pass(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
     const size_t chunk   = std::min<size_t>(n, 1u << 16);
     GatherRecord* d_recs = nullptr;
     uint32_t* d_vox      = nullptr;
@@ -212,9 +288,103 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     return 0;
   }
 
+  // Streamer::streamInToGPU (streamer.cpp:358-378) for a selection of host-store records.
+  int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
+    if (n == 0)
+      return 0;
+    uint32_t n_low = 0;
+    for (size_t i = 0; i < n; ++i)
+      n_low += recs[i].resolution != 0;
+    if (carve_low_blocks(m, n_low))
+      return 1;
+    // Records that repeat a key (a block paged out, allocated again, paged out again) must not race
+    // with the record that creates the block: the k-th copy of a key goes into pass k.
+    std::unordered_map<unsigned long long, uint32_t> seen;
+    seen.reserve(2 * n);
+    std::vector<uint32_t> pass(n);
+    uint32_t n_pass = 1;
+    for (size_t i = 0; i < n; ++i) {
+      const unsigned long long key = ((unsigned long long) (uint32_t) (recs[i].x + kCoordBias) << 42) | ((unsigned long long) (uint32_t) (recs[i].y + kCoordBias) << 21) | (unsigned long long) (uint32_t) (recs[i].z + kCoordBias);
+      pass[i] = seen[key]++;
+      n_pass  = std::max(n_pass, pass[i] + 1);
+    }
+    if (n_pass == 1)
+      return insert_pass(m, recs, voxels, n);
+    const size_t words = (size_t) 3 * kBlockVoxels;
+    for (uint32_t p = 0; p < n_pass; ++p) {
+      std::vector<GatherRecord> r;
+      std::vector<uint32_t> v;
+      for (size_t i = 0; i < n; ++i)
+        if (pass[i] == p) {
+          r.push_back(recs[i]);
+          v.insert(v.end(), voxels + i * words, voxels + (i + 1) * words);
+        }
+      if (insert_pass(m, r.data(), v.data(), r.size()))
+        return 1;
+    }
+    return 0;
+  }
+
+  // Streamer::worldToChunks (streamer.cuh:251-260) of a block origin (streamer.cpp:231-233), then
+  // isChunkInSphere (streamer.cuh:346-352) of that chunk
+  bool record_in_sphere(const mrh_map* m, const GatherRecord& r, const float centre[3], float radius) {
+    const float size = m->p.virtual_voxel_size, ext = (float) m->p.voxel_extents_scale;
+    const float chunk_radius = 0.5f * ext * std::sqrt(3.f); // streamer.cpp:15
+    const int pos[3] = {r.x, r.y, r.z};
+    float d[3];
+    for (int k = 0; k < 3; ++k) {
+      const float pw = ((float) pos[k] * 8.f) * size;
+      const float p  = pw / ext;
+      const float sg = (float) ((0.f < p) - (p < 0.f));
+      const int c    = (int) (p + sg * 0.5f);
+      d[k]           = (float) c * ext - centre[k];
+    }
+    const float l = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    return l <= std::fabs(radius - chunk_radius);
+  }
+
+  int stream_radius(mrh_map* m, const float centre[3], float radius) {
+    HostStore& st = m->store;
+    // stream out (streamOutToHostPass0 + integrateInChunkGrid): blocks >= radius away go to the store
+    const size_t before = st.recs.size();
+    if (gather_to_host(m, st.recs, st.voxels, centre, radius))
+      return 1;
+    m->last_stream_out = st.recs.size() - before;
+    // stream in (streamInToGPU / integrateInHash): every stored block whose chunk lies in the sphere
+    std::vector<GatherRecord> in_recs, keep_recs;
+    std::vector<uint32_t> in_vox, keep_vox;
+    const size_t words = (size_t) 3 * kBlockVoxels;
+    for (size_t i = 0; i < st.recs.size(); ++i) {
+      const bool in = i < before && record_in_sphere(m, st.recs[i], centre, radius); // what just left stays out
+      (in ? in_recs : keep_recs).push_back(st.recs[i]);
+      std::vector<uint32_t>& vv = in ? in_vox : keep_vox;
+      vv.insert(vv.end(), st.voxels.begin() + i * words, st.voxels.begin() + (i + 1) * words);
+    }
+    m->last_stream_in = in_recs.size();
+    if (!in_recs.empty()) {
+      mrh_stats s0, s1;
+      if (mrh_get_stats(m, &s0) || insert_from_host(m, in_recs.data(), in_vox.data(), in_recs.size()) || mrh_get_stats(m, &s1))
+        return 1;
+      // keys that were allocated again while their old block sat in the store: fused (k_insert_blocks)
+      m->stream_duplicates += in_recs.size() - (size_t) (s1.blocks_new - s0.blocks_new);
+      st.recs.swap(keep_recs);
+      st.voxels.swap(keep_vox);
+    }
+    m->stream_events++;
+    m->counters_clean = false;
+    return 0;
+  }
+
 } // namespace mrh
 
 extern "C" {
+
+int mrh_stream(mrh_map* m, const float centre[3], float radius) {
+  if (!m || !centre)
+    return fail("null argument");
+  CK(cudaSetDevice(m->device));
+  return stream_radius(m, centre, radius);
+}
 
 int mrh_dump_state(mrh_map* m, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out) {
   if (!m || !n_out)
@@ -271,6 +441,21 @@ int mrh_store_append(mrh_map* m, const mrh_dump_entry* entries, const void* voxe
   for (size_t i = 0; i < n; ++i)
     st.recs[base + i] = {entries[i].x, entries[i].y, entries[i].z, entries[i].resolution, entries[i].ptr};
   memcpy(st.voxels.data() + base * 3 * kBlockVoxels, voxels, n * 12 * kBlockVoxels);
+  return 0;
+}
+
+int mrh_store_read(mrh_map* m, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out) {
+  if (!m || !n_out)
+    return fail("null argument");
+  const HostStore& st = m->store;
+  *n_out              = st.recs.size();
+  if (!entries)
+    return 0;
+  const size_t n = std::min(max_entries, st.recs.size());
+  for (size_t i = 0; i < n; ++i)
+    entries[i] = {st.recs[i].x, st.recs[i].y, st.recs[i].z, st.recs[i].resolution, st.recs[i].ptr};
+  if (voxels && n)
+    memcpy(voxels, st.voxels.data(), n * 12 * kBlockVoxels);
   return 0;
 }
 

@@ -50,6 +50,7 @@ struct Counters {
   unsigned long long dropped_heap;   // allocBlock "mem size exceed" events
   unsigned long long dropped_table;  // probe sequence exhausted / coordinate out of key range
   unsigned long long dropped_updates; // point-cloud records beyond the staging capacity
+  unsigned long long stream_merged;   // streamed-in blocks whose key was live again: fused into the live block
   // map state (not reset by mrh_reset_stats)
   unsigned long long low_parents;    // pool blocks carved into 64-voxel sub-slots
   unsigned long long low_live;       // live resolution-1 blocks

@@ -291,6 +291,13 @@ class GeoWrapper:
     def synchronize(self):
         check(self._lib.mrh_synchronize(self._h))
 
+    def stream(self, centre, radius):
+        """Streamer::stream (streamer.cpp:337-355): page blocks farther than `radius` from `centre` out to
+        the host store and the stored blocks around `centre` back in. compute() does this by itself
+        when the pool runs low (field StreamThreshold)."""
+        c = _f32(centre).reshape(3)
+        check(self._lib.mrh_stream(self._h, c.ctypes.data_as(_capi._fp), float(radius)))
+
     def streamAllOut(self):
         check(self._lib.mrh_stream_all_out(self._h))
 
@@ -383,6 +390,16 @@ class GeoWrapper:
         n = C.c_size_t()
         check(self._lib.mrh_store_size(self._h, C.byref(n)))
         return n.value
+
+    def storeDump(self):
+        """(entries [n,5] int32, voxels [n,512]) of the host store, in store order."""
+        n = C.c_size_t()
+        check(self._lib.mrh_store_read(self._h, None, None, 0, C.byref(n)))
+        entries = np.zeros((n.value, 5), np.int32)
+        voxels = np.zeros((n.value, 512), VOXEL_DTYPE)
+        if n.value:
+            check(self._lib.mrh_store_read(self._h, entries.ctypes.data, voxels.ctypes.data, n.value, C.byref(n)))
+        return entries, voxels
 
     def storeAppend(self, entries, voxels):
         """Add blocks (as dumpState returns them, e.g. another shard's) to the host store."""
