@@ -125,8 +125,6 @@ static void free_map(mrh_map* m) {
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
   cudaFreeHost(m->h_heap_probe);
-  if (m->ev_probe)
-    cudaEventDestroy(m->ev_probe);
   for (int i = 0; i < 8; ++i)
     if (m->ev_k[i])
       cudaEventDestroy(m->ev_k[i]);
@@ -269,8 +267,9 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
       CK(cudaEventCreateWithFlags(&in->consumed[i], cudaEventDisableTiming));
     }
   CK(cudaMallocHost(&m->h_ctr, sizeof(Counters)));
-  CK(cudaMallocHost(&m->h_heap_probe, sizeof(int)));
-  CK(cudaEventCreateWithFlags(&m->ev_probe, cudaEventDisableTiming));
+  CK(cudaMallocHost(&m->h_heap_probe, 2 * sizeof(int)));
+  m->h_heap_probe[0] = 0x7FFFFFF0, m->h_heap_probe[1] = -1;
+  m->dev.host_probe  = m->h_heap_probe;
   for (int i = 0; i < 8; ++i)
     CK(cudaEventCreate(&m->ev_k[i]));
   cudaDeviceProp prop;
@@ -467,9 +466,9 @@ static int compute_frame(mrh_map* m) {
   refresh_map_params(m);
   // GeoWrapper::compute (geowrapper.cpp:137-138): page when the pool runs low. The free count is the
   // one probed at the end of the last frame whose probe has arrived (no device wait here).
-  if (m->probe_valid && m->stream_threshold > 0.f && cudaEventQuery(m->ev_probe) == cudaSuccess) {
-    m->probe_valid = false;
-    if ((double) (*m->h_heap_probe + 1) <= (double) m->stream_threshold * (double) m->num_sdf_blocks) {
+  if (m->stream_threshold > 0.f && m->frames_probe_seen != ((volatile int*) m->h_heap_probe)[1]) {
+    m->frames_probe_seen = ((volatile int*) m->h_heap_probe)[1];
+    if ((double) (((volatile int*) m->h_heap_probe)[0] + 1) <= (double) m->stream_threshold * (double) m->num_sdf_blocks) {
       const float centre[3] = {m->pose[3], m->pose[7], m->pose[11]};
       if (stream_radius(m, centre, m->cam.max_depth))
         return 1;
@@ -492,11 +491,6 @@ static int compute_frame(mrh_map* m) {
   if (m->n_points && integrate_points(m))
     return 1;
   CK(cudaEventRecord(m->ev1, m->stream));
-  if (m->stream_threshold > 0.f && !m->pending_gc) {
-    CK(cudaMemcpyAsync(m->h_heap_probe, &m->dev.ctr->heap_counter, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaEventRecord(m->ev_probe, m->stream));
-    m->probe_valid = true;
-  }
   for (Ingest* in : used)
     if (in && in->active)
       CK(cudaEventRecord(in->consumed[in->which], m->stream));

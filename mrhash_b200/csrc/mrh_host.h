@@ -121,11 +121,10 @@ struct mrh_map {
   uint32_t halo_owned    = 0;
   uint16_t* d_shell_idx  = nullptr;
   // radius paging (Streamer::stream): trigger when free pool blocks <= stream_threshold * num_sdf_blocks
-  // (params.h:28); the free count is probed asynchronously at the end of every frame
+  // (params.h:28); the last kernel of a frame writes {free-stack top, frame tag} into pinned host memory
   float stream_threshold  = 0.15f;
-  int* h_heap_probe       = nullptr; // pinned
-  cudaEvent_t ev_probe    = nullptr;
-  bool probe_valid        = false;
+  int* h_heap_probe       = nullptr; // pinned, 2 ints
+  int frames_probe_seen   = -1;
   uint64_t stream_events = 0, last_stream_out = 0, last_stream_in = 0, stream_duplicates = 0;
   mrh::HostStore store;
   mrh::HostMesh mesh;

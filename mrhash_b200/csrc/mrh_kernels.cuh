@@ -338,6 +338,13 @@ __global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraD
         m.ctr->live_count[f.live_cur] = 0; // next frame's output list
         m.ctr->vis_count              = 0;
         m.ctr->done_ctas              = 0;
+        // paging trigger (GeoWrapper::compute, geowrapper.cpp:137): the host looks at these two words
+        // before the next frame, no copy engine operation and no wait involved
+        if (f.pad[0]) { // host asks for it every 16th frame, every frame once the pool is below 40 % free
+          m.host_probe[0] = *reinterpret_cast<volatile int*>(&m.ctr->heap_counter);
+          m.host_probe[1] = (int) f.frame_index;
+          __threadfence_system();
+        }
       }
     }
   }
@@ -383,6 +390,13 @@ __global__ void __launch_bounds__(128) k_starve(MapDev m, FrameDev f, CameraDev 
       }
     }
   }
+}
+
+// end-of-frame probe for the paths whose last kernel does not write it (see k_integrate)
+__global__ void k_probe(MapDev m, uint32_t frame_index) {
+  m.host_probe[0] = m.ctr->heap_counter;
+  m.host_probe[1] = (int) frame_index;
+  __threadfence_system();
 }
 
 // recompute the GC statistics of every visible block from its payload (starve / variance frames)

@@ -118,6 +118,7 @@ struct MapDev {
   unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate
   unsigned long long* zbuf;
   Counters* ctr;
+  int* host_probe; // pinned host memory (UVA): {free-stack top, frame tag} written at the end of a frame for the paging trigger
 };
 
 // The pose straight out of the kernel parameters (constant bank): no shared-memory staging, no barrier.
