@@ -49,6 +49,12 @@ def test_marching_cubes_matches_reference(tmp_path):
     f0 = lines[hdr_end + 1 + len(ours.getVertices())].split()
     assert f0[0] == "3" and [int(x) for x in f0[1:]] == ours.getFaces()[0].tolist()
     assert len(lines) == hdr_end + 1 + len(ours.getVertices()) + len(ours.getFaces()) + 1
+    # every vertex and face line, byte for byte, against printf's %g / %d (csrc/mrh_fmt.h is a fast exact %g)
+    Vp, Fp, Cp = ours.getVertices(), ours.getFaces(), ours.getColors()
+    want_v = ["%g %g %g %d %d %d" % (v[0], v[1], v[2], int(c[0]) & 0xFF, int(c[1]) & 0xFF, int(c[2]) & 0xFF) for v, c in zip(Vp.tolist(), Cp.tolist())]
+    assert lines[hdr_end + 1 : hdr_end + 1 + len(Vp)] == want_v
+    want_f = ["3 %d %d %d" % tuple(f) for f in Fp.tolist()]
+    assert lines[hdr_end + 1 + len(Vp) : hdr_end + 1 + len(Vp) + len(Fp)] == want_f
     mine = ours.getTriangles()
     assert len(mine) > 10000
     # every block left the device (streamAllOut inside extractMesh) and sits in the host store
