@@ -15,7 +15,10 @@ allocation -> visibility -> TSDF fusion + garbage collection.
 `--impl reference` runs the UNMODIFIED reference kernels (oracle/_ref/libref_harness.so, compiled
 from /root/reference for sm_100a) on the same stream, host buffers in, the way GeoWrapper::compute
 drives them. N>1 (torchrun): the map is sharded by hash-bucket range, rank 0 ingests each frame and
-broadcasts it over NCCL; every rank allocates / fuses only the blocks it owns.
+broadcasts it over NCCL; every rank allocates / fuses only the blocks it owns (starve frames
+min-reduce the z-buffer over the ranks). Two more keys at N>1: `replica_streams` (one unsharded
+stream per GPU, no collective) and `sharded_mesh` (boundary exchange + marching cubes in place +
+soup gather + weld, timed). stdout carries exactly one JSON line; everything else goes to stderr.
 """
 import argparse
 import json
@@ -33,7 +36,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
-COUNTERS_BYTES = 120  # sizeof(mrh::Counters)
+COUNTERS_BYTES = 136  # sizeof(mrh::Counters), the read-back of getStats()
 
 
 def parse():
@@ -389,24 +392,23 @@ def main():
             host_us["compute"] += c2 - c1
             host_us["read_result"] += c3 - c2
             return st
+        # N > 1: rank 0 ingests the frame from its host buffers; the others receive it over NVLink.
+        # The copy + broadcast run on torch's stream; the handle's stream is ordered after them
+        # (and the next broadcast after this frame's kernels) with events only.
         g.setCurrPose(*poses[k])
-        if True:
-            # rank 0 ingests the frame from its host buffers; the others receive it over NVLink.
-            # The copy + broadcast run on torch's stream; the handle's stream is ordered after them
-            # (and the next broadcast after this frame's kernels) with events only.
-            torch.cuda.current_stream().wait_event(ev_done)
-            if rank == 0:
-                bcast_d.copy_(depth_h[k], non_blocking=True)
-                bcast_c.copy_(rgb_h[k], non_blocking=True)
-            dist.broadcast(bcast_d, 0)
-            dist.broadcast(bcast_c, 0)
-            ev_ready.record()
-            stream.wait_event(ev_ready)
-            g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
-            g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
-            run_frame(g)
-            ev_done.record(stream)
-            return g.getStats()
+        torch.cuda.current_stream().wait_event(ev_done)
+        if rank == 0:
+            bcast_d.copy_(depth_h[k], non_blocking=True)
+            bcast_c.copy_(rgb_h[k], non_blocking=True)
+        dist.broadcast(bcast_d, 0)
+        dist.broadcast(bcast_c, 0)
+        ev_ready.record()
+        stream.wait_event(ev_ready)
+        g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
+        g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
+        run_frame(g)
+        ev_done.record(stream)
+        return g.getStats()
 
     for k in range(W):
         step_host(k)

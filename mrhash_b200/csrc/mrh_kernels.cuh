@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(256) k_alloc_rgbd(MapDev m, FrameDev f, Camera
     }
   }
   __syncthreads();
-  const unsigned full = 0xFFFFFFFFu;
   const int lane      = threadIdx.x & 31;
   const int warp      = threadIdx.x >> 5;
   const uint32_t col  = blockIdx.x * 32 + lane;
