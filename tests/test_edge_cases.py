@@ -176,3 +176,34 @@ def test_1280x960_frames_match_reference_kernels():
         feed(ours, [orc, ref], t, q, depth, rgb)
     rep = compare_dumps(ours.dumpState(), ref.dump())
     assert rep["ok"] and rep["sdf_bitexact"], rep
+
+
+def test_extract_mesh_over_several_streaming_regions():
+    """extractMesh walks the chunk bounds in steps of 10 x max_depth (geowrapper.cpp:161-186) and
+    streams one sphere of chunks in per step; a small max_depth at extraction time forces several
+    regions. Their soups are accumulated on the device and welded once; triangles meshed by two
+    overlapping regions collapse in the weld, and every block is back in the host store afterwards."""
+    def build():
+        g, p = small_map(320, 240, num_sdf_blocks=60000, hash_num_buckets=30000, max_num_triangles=400000)
+        for k in range(6):
+            t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000, width=320, height=240)
+            g.setCurrPose(t, q)
+            g.setDepthImage(depth)
+            g.setRGBImage(rgb)
+            g.compute()
+        return g, p
+
+    one, p = build()
+    n_blocks = one.getStats()["live_blocks"]
+    one.extractMesh(None)
+    t_one, v_one = len(one.getTriangles()), len(one.getVertices())
+    many, _ = build()
+    fx, fy, cx, cy = synth.intrinsics(320, 240)
+    many.setCamera(fx, fy, cx, cy, 240, 320, p["min_depth"], 0.25, 0)  # region step int(10 * 0.25) = 2 chunks
+    many.extractMesh(None)
+    V, F = many.getVertices(), many.getFaces()
+    print(f"[regions] one region: {t_one} triangles / {v_one} vertices; several regions: {len(many.getTriangles())} triangles in the last region, welded {len(V)} vertices / {len(F)} faces")
+    assert many.storeSize() == n_blocks and many.getStats()["live_blocks"] == 0
+    assert len(V) > 0.5 * v_one and len(V) <= 1.05 * v_one
+    assert len(np.unique(V, axis=0)) == len(V) and F.max() < len(V)
+    assert len(np.unique(F, axis=0)) == len(F)
