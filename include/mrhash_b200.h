@@ -182,6 +182,17 @@ int mrh_weld_device_soup(mrh_map* m, const float* d_soup, size_t n_triangles, co
 
 /* GeoWrapper::serializeData (geowrapper.cpp:563-565) */
 int mrh_serialize_data(mrh_map* m, const char* hash_path, const char* voxel_path);
+/* GeoWrapper::serializeGrid / deserializeGrid (geowrapper.cpp:567-573): the host store (what streamAllOut
+ * leaves behind) as a checkpoint file in the reference's own format - Serializer<Voxel> (serializer.h:16-75):
+ * per 1 m chunk `u64 size | int32 chunk[3] | cista::offset bytes of ChunkDesc<Voxel>` - so that files move
+ * between the reference and this library in both directions. deserialize replaces the chunks the file
+ * names and keeps the rest of the store. */
+int mrh_serialize_grid(mrh_map* m, const char* path);
+int mrh_deserialize_grid(mrh_map* m, const char* path);
+/* the same format without a handle (no device needed): records as in mrh_dump_state, 512 x 12-byte
+ * voxels per record (a resolution-1 record uses the first 64) */
+int mrh_grid_write(const char* path, const mrh_dump_entry* entries, const void* voxels, size_t n, float virtual_voxel_size, float voxel_extents);
+int mrh_grid_read(const char* path, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out);
 /* GeoWrapper::clearBuffers (geowrapper.cpp:552-557) */
 int mrh_clear_buffers(mrh_map* m);
 

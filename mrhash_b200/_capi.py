@@ -102,6 +102,10 @@ SIGNATURES = {
     "mrh_get_mesh": ([_vp, _P(_P(C.c_double)), _P(_P(C.c_int32)), _P(_P(C.c_double)), _P(C.c_size_t), _P(C.c_size_t)], _i),
     "mrh_get_triangles": ([_vp, _P(_fp), _P(C.c_size_t)], _i),
     "mrh_serialize_data": ([_vp, C.c_char_p, C.c_char_p], _i),
+    "mrh_serialize_grid": ([_vp, C.c_char_p], _i),
+    "mrh_deserialize_grid": ([_vp, C.c_char_p], _i),
+    "mrh_grid_write": ([C.c_char_p, _vp, _vp, C.c_size_t, _f, _f], _i),
+    "mrh_grid_read": ([C.c_char_p, _vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),
     "mrh_clear_buffers": ([_vp], _i),
     "mrh_get_field": ([_vp, C.c_char_p, _P(C.c_double)], _i),
     "mrh_set_field": ([_vp, C.c_char_p, C.c_double], _i),

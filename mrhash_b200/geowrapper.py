@@ -338,10 +338,12 @@ class GeoWrapper:
         check(self._lib.mrh_serialize_data(self._h, str(filename_hash).encode(), str(filename_voxel).encode()))
 
     def serializeGrid(self, filename="./data/grid.bin"):
-        raise RuntimeError("GeoWrapper::serializeGrid | cista checkpoint format is out of scope of mrhash_b200 (SURVEY.md §8f-3)")
+        """geowrapper.cpp:567-569: the host chunk grid as a checkpoint in the reference's file format."""
+        check(self._lib.mrh_serialize_grid(self._h, str(filename).encode()))
 
     def deserializeGrid(self, filename="./data/grid.bin"):
-        raise RuntimeError("GeoWrapper::deserializeGrid | cista checkpoint format is out of scope of mrhash_b200 (SURVEY.md §8f-3)")
+        """geowrapper.cpp:571-573: chunks of the file replace the same chunks of the host store."""
+        check(self._lib.mrh_deserialize_grid(self._h, str(filename).encode()))
 
     def clearBuffers(self):
         check(self._lib.mrh_clear_buffers(self._h))
@@ -482,6 +484,26 @@ class GeoWrapper:
             check(self._lib.mrh_dump_state(self._h, entries.ctypes.data, voxels.ctypes.data, n.value, C.byref(m)))
             entries, voxels = entries[: m.value], voxels[: m.value]
         return entries, voxels
+
+
+def grid_write(path, entries, voxels, virtual_voxel_size, voxel_extents=1.0):
+    """serializeGrid's file format without a handle (no GPU needed): entries [n,5] int32, voxels [n,512]."""
+    e = np.ascontiguousarray(entries, np.int32)
+    v = np.ascontiguousarray(voxels)
+    assert e.ndim == 2 and e.shape[1] == 5 and v.shape == (len(e), 512) and v.dtype == VOXEL_DTYPE
+    check(_capi.lib().mrh_grid_write(str(path).encode(), e.ctypes.data, v.ctypes.data, len(e), float(virtual_voxel_size), float(voxel_extents)))
+
+
+def grid_read(path):
+    """(entries [n,5] int32, voxels [n,512]) of a serializeGrid file, in file order."""
+    lib = _capi.lib()
+    n = C.c_size_t()
+    check(lib.mrh_grid_read(str(path).encode(), None, None, 0, C.byref(n)))
+    entries = np.zeros((n.value, 5), np.int32)
+    voxels = np.zeros((n.value, 512), VOXEL_DTYPE)
+    if n.value:
+        check(lib.mrh_grid_read(str(path).encode(), entries.ctypes.data, voxels.ctypes.data, n.value, C.byref(n)))
+    return entries, voxels
 
 
 # voxel_hash_utils.cuh:8-22

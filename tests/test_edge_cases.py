@@ -74,8 +74,8 @@ def test_argument_errors_use_the_reference_messages():
     g.setRGBImage(np.zeros((60, 80, 3), np.uint8))
     with pytest.raises(RuntimeError, match="do not match the camera"):
         g.compute()
-    with pytest.raises(RuntimeError):
-        g.serializeGrid("/tmp/x.bin")
+    with pytest.raises(RuntimeError, match="Failed to open file for writing"):
+        g.serializeGrid("/nonexistent-dir/x.bin")
 
 
 def test_float_rgb_is_cast_like_the_binding():

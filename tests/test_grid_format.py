@@ -1,0 +1,105 @@
+"""CPU: serializeGrid / deserializeGrid file format (csrc/mrh_grid.cu, no device needed) pinned
+against a checkpoint written by the reference's own serialization library: tests/golden/grid_cista.bin
+comes from cista (the reference's vendored utils/cista.h, compiled into oracle/_ref/cista_grid_tool) with
+the record types of streamer.cuh:21-165 and the framing of serializer.h:16-75
+(tests/golden/make_grid_golden.py)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from mrhash_b200 import VOXEL_DTYPE
+from mrhash_b200.geowrapper import grid_read, grid_write
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "grid_cista.bin")
+TOOL = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "cista_grid_tool")
+
+
+def golden_blocks():
+    z = np.load(os.path.join(HERE, "golden", "grid_cista.npz"))
+    return z["entries"], z["voxels"].view(VOXEL_DTYPE).reshape(len(z["entries"]), 512), float(z["voxel_size"]), float(z["extents"])
+
+
+def records(path):
+    """{chunk: bytes} of a grid file (the chunk order of a file is the iteration order of an unordered_map)."""
+    data, out, off = open(path, "rb").read(), {}, 0
+    while off < len(data):
+        (size,) = struct.unpack_from("<Q", data, off)
+        chunk = struct.unpack_from("<3i", data, off + 8)
+        assert chunk not in out
+        out[chunk] = data[off + 20 : off + 20 + size]
+        off += 20 + size
+    assert off == len(data)
+    return out
+
+
+def by_key(entries, voxels):
+    return {tuple(e[:3]): (tuple(e[3:]), v.tobytes()) for e, v in zip(entries.tolist(), voxels)}
+
+
+def test_reader_decodes_the_cista_file():
+    entries, voxels, _, _ = golden_blocks()
+    e, v = grid_read(GOLD)
+    assert len(e) == len(entries) and (e[:, 3] == 1).sum() > 3
+    assert by_key(e, v) == by_key(entries, voxels)
+
+
+def test_writer_reproduces_the_cista_file_byte_for_byte(tmp_path):
+    entries, voxels, size, ext = golden_blocks()
+    path = str(tmp_path / "grid.bin")
+    grid_write(path, entries, voxels, size, ext)
+    mine, gold = records(path), records(GOLD)
+    assert set(mine) == set(gold) and len(gold) > 10
+    for chunk in gold:
+        assert mine[chunk] == gold[chunk], chunk
+    assert os.path.getsize(path) == os.path.getsize(GOLD)
+
+
+def test_round_trip_and_errors(tmp_path):
+    rng = np.random.default_rng(3)
+    n = 300
+    pos = np.unique(rng.integers(-200, 200, size=(n, 3)), axis=0).astype(np.int32)
+    entries = np.concatenate([pos, np.zeros((len(pos), 1), np.int32), (np.arange(len(pos))[:, None] * 512).astype(np.int32)], axis=1)
+    voxels = rng.integers(0, 256, size=(len(pos), 512 * 12), dtype=np.uint8).view(VOXEL_DTYPE).reshape(len(pos), 512)
+    path = str(tmp_path / "rt.bin")
+    grid_write(path, entries, voxels, 0.2, 1.0)
+    e, v = grid_read(path)
+    assert by_key(e, v) == by_key(entries, voxels)
+    grid_write(str(tmp_path / "empty.bin"), entries[:0], voxels[:0], 0.2, 1.0)
+    assert len(grid_read(str(tmp_path / "empty.bin"))[0]) == 0
+    with pytest.raises(RuntimeError, match="Failed to open file for reading"):
+        grid_read(str(tmp_path / "missing.bin"))
+    # a truncated / corrupted file is reported, not read past its end
+    data = open(path, "rb").read()
+    open(str(tmp_path / "cut.bin"), "wb").write(data[: len(data) // 2 + 30])
+    with pytest.raises(RuntimeError, match="Read failed|Corrupted"):
+        grid_read(str(tmp_path / "cut.bin"))
+    bad = bytearray(data)
+    bad[20:28] = struct.pack("<q", 1 << 40)  # first vector header points far outside its record
+    open(str(tmp_path / "bad.bin"), "wb").write(bytes(bad))
+    with pytest.raises(RuntimeError, match="Corrupted"):
+        grid_read(str(tmp_path / "bad.bin"))
+
+
+@pytest.mark.skipif(not os.path.exists(TOOL), reason="oracle/_ref/cista_grid_tool not built (needs /root/reference)")
+def test_cista_itself_reads_what_the_writer_produces(tmp_path):
+    """The other direction: cista::deserialize (through the tool) decodes a file of our writer."""
+    entries, voxels, size, ext = golden_blocks()
+    path, back = str(tmp_path / "grid.bin"), str(tmp_path / "blocks.bin")
+    grid_write(path, entries, voxels, size, ext)
+    subprocess.check_call([TOOL, "decode", path, back])
+    data = open(back, "rb").read()
+    (n,) = struct.unpack_from("<I", data, 0)
+    assert n == len(entries)
+    off, seen = 4, {}
+    for _ in range(n):
+        c0, c1, c2, x, y, z, ptr, res, nv = struct.unpack_from("<3i3iiiI", data, off)
+        off += 36
+        assert nv == (512 if res == 0 else 64)
+        seen[(x, y, z)] = ((res, ptr), data[off : off + 12 * nv])
+        off += 12 * nv
+    want = {k: (a, b[: 12 * (512 if a[0] == 0 else 64)]) for k, (a, b) in by_key(entries, voxels).items()}
+    assert seen == want

@@ -115,3 +115,36 @@ def test_explicit_stream_round_trip():
     feed(g, 6)
     rep = compare_dumps(g.dumpState(), h.dumpState())
     assert rep["ok"] and rep["sdf_bitexact"], rep
+
+
+def test_serialize_grid_checkpoint_round_trip(tmp_path):
+    """serializeGrid / deserializeGrid (geowrapper.cpp:567-573) through the handle: a map leaves the
+    device, goes to a checkpoint in the reference's file format (pinned byte for byte against cista in
+    tests/test_grid_format.py), comes back into a fresh handle and continues exactly as the original."""
+    from mrhash_b200.geowrapper import grid_read
+
+    a = make(40000, 0.0)
+    for k in range(6):
+        t = feed(a, k)
+    before = a.dumpState()
+    path = str(tmp_path / "grid.bin")
+    a.streamAllOut()
+    a.serializeGrid(path)
+    e, v = grid_read(path)
+    assert len(e) == len(before[0]) and {tuple(x[:3]) for x in e.tolist()} == {tuple(x[:3]) for x in before[0].tolist()}
+    b = make(40000, 0.0)
+    b.deserializeGrid(path)
+    assert b.storeSize() == len(before[0])
+    b.deserializeGrid(path)  # chunks of the file replace the same chunks: reading twice does not double anything
+    assert b.storeSize() == len(before[0])
+    b.stream(t, 1e6)  # page everything in
+    rep = compare_dumps(b.dumpState(), before)
+    assert rep["ok"] and rep["sdf_bitexact"] and rep["sum_squared_bitexact"], rep
+    # the restored map integrates the next frame exactly like a map that never left the device
+    c = make(40000, 0.0)
+    for k in range(7):
+        feed(c, k)
+    b._lib.mrh_set_field(b._h, b"NFramesInvalidateVoxels", 0.0)
+    feed(b, 6)
+    rep = compare_dumps(b.dumpState(), c.dumpState())
+    assert rep["ok"] and rep["sdf_bitexact"], rep
