@@ -430,6 +430,27 @@ def main():
     if world == 1:
         g.close()
 
+    # ---------------- pass B': the same from PAGEABLE numpy arrays (what rgbd_runner.py hands over) --
+    e2e_pageable = None
+    if world == 1:
+        Kq = min(K, 300)
+        depth_pg = [np.array(depth_np[W + i]) for i in range(Kq)]  # fresh pageable copies
+        rgb_pg = [np.array(rgb_np[W + i]) for i in range(Kq)]
+        g = new_map(args, rank, world, local)
+        for k in range(W):
+            step_host(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Kq):
+            g.setCurrPose(*poses[W + i])
+            g.setDepthImage(depth_pg[i])
+            g.setRGBImage(rgb_pg[i])
+            g.compute()
+            g.getStats()
+        dt = time.perf_counter() - t0
+        e2e_pageable = {"value": Kq / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / Kq, "steps": Kq, "what": "inputs in pageable host memory: staged through pinned buffers inside the setters"}
+        g.close()
+
     # ---------------- N > 1 only: (i) one independent stream per GPU, (ii) sharded meshing ------------
     extra_multi = {}
     if world > 1:
@@ -548,6 +569,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if e2e_pageable is not None:
+            line["e2e_pageable"] = e2e_pageable
         line.update(extra_multi)
         print(json.dumps(line), flush=True)
     if world > 1:

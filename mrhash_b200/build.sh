@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/csrc"
 NVCC=${NVCC:-nvcc}
-FLAGS="-std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC,-O2,-Wall"
+FLAGS="-std=c++17 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC,-O2,-Wall,-fopenmp"
 mkdir -p ../_build
 pids=()
 for f in mrh_capi mrh_frame mrh_state mrh_mesh mrh_weld mrh_halo mrh_grid; do
@@ -14,5 +14,5 @@ for f in mrh_capi mrh_frame mrh_state mrh_mesh mrh_weld mrh_halo mrh_grid; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o ../libmrhash_b200.so ../_build/*.o -lcudart
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC -o ../libmrhash_b200.so ../_build/*.o -lcudart -lgomp
 echo "built $(realpath ../libmrhash_b200.so)"

@@ -4,6 +4,7 @@
 // VoxelContainer::integrate() (voxel_data_structures.cpp:90-134): one stream, no host
 // synchronisation inside a frame, no per-frame allocation, pinned double-buffered ingest.
 #include <algorithm>
+#include <thread>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -168,6 +169,32 @@ static void refresh_map_params(mrh_map* m) {
 // returns once the bytes are staged (setters copy: the caller may reuse its buffer on return).
 // Page-locked caller memory is read by DMA directly; that transfer is only waited for at the end of
 // compute(), so such a buffer must stay unchanged until compute() returns (include/mrhash_b200.h).
+// Staging copy of a pageable frame: the source is cold (a freshly decoded image), so one thread gets
+// ~10 GB/s out of it and the copy, not the transfer, is what the setter waits for; a few threads in
+// 256 KB slices bring it close to the memory system's rate.
+static int copy_threads() {
+  static const int n = [] {
+    const char* e = getenv("MRH_COPY_THREADS"); // tuning knob; default: 8, at most half of the machine
+    const int hw  = (int) std::thread::hardware_concurrency();
+    const int v   = e ? atoi(e) : 8;
+    return std::max(1, std::min(v, std::max(1, hw / 2)));
+  }();
+  return n;
+}
+static void staged_copy(void* dst, const void* src, size_t bytes) {
+  const size_t slice = 256u << 10;
+  const long n       = (long) ((bytes + slice - 1) / slice);
+  if (n <= 2) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+#pragma omp parallel for num_threads(copy_threads()) schedule(static)
+  for (long i = 0; i < n; ++i) {
+    const size_t o = (size_t) i * slice;
+    memcpy((char*) dst + o, (const char*) src + o, std::min(slice, bytes - o));
+  }
+}
+
 template <typename T, typename F>
 static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n, F fill) {
   if (in.pending_direct) { // set twice without a compute() in between
@@ -392,7 +419,7 @@ int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols) {
   if (!depth || rows <= 0 || cols <= 0)
     return fail("GeoWrapper::setDepthImage|input should be a 2D numpy array");
   const size_t n = (size_t) rows * cols;
-  if (ingest_upload<float>(m, m->in_depth, depth, n, [&](float* dst) { memcpy(dst, depth, sizeof(float) * n); }))
+  if (ingest_upload<float>(m, m->in_depth, depth, n, [&](float* dst) { staged_copy(dst, depth, sizeof(float) * n); }))
     return 1;
   m->depth_ptr = (const float*) m->in_depth.d_buf[m->in_depth.which], m->depth_rows = rows, m->depth_cols = cols;
   return 0;
@@ -403,7 +430,7 @@ int mrh_set_rgb(mrh_map* m, const uint8_t* rgb, int rows, int cols) {
   if (!rgb || rows <= 0 || cols <= 0)
     return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
   const size_t n = (size_t) rows * cols * 3;
-  if (ingest_upload<uint8_t>(m, m->in_rgb, rgb, n, [&](uint8_t* dst) { memcpy(dst, rgb, n); }))
+  if (ingest_upload<uint8_t>(m, m->in_rgb, rgb, n, [&](uint8_t* dst) { staged_copy(dst, rgb, n); }))
     return 1;
   m->rgb_ptr = (const uint8_t*) m->in_rgb.d_buf[m->in_rgb.which], m->rgb_rows = rows, m->rgb_cols = cols;
   return 0;
@@ -415,7 +442,8 @@ int mrh_set_rgb_f32(mrh_map* m, const float* rgb, int rows, int cols) {
     return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
   const size_t n = (size_t) rows * cols * 3;
   if (ingest_upload<uint8_t>(m, m->in_rgb, nullptr, n, [&](uint8_t* dst) {
-        for (size_t i = 0; i < n; ++i)
+#pragma omp parallel for num_threads(copy_threads()) schedule(static)
+        for (long i = 0; i < (long) n; ++i)
           dst[i] = (uint8_t) rgb[i];
       }))
     return 1;
@@ -450,7 +478,7 @@ int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* norma
   }
   if (!m->p.projective_sdf)
     return fail("mrh_set_points: only projective_sdf=True is implemented (every shipped runner uses it)");
-  if (ingest_upload<float>(m, m->in_points, points, n * 3, [&](float* dst) { memcpy(dst, points, sizeof(float) * n * 3); }))
+  if (ingest_upload<float>(m, m->in_points, points, n * 3, [&](float* dst) { staged_copy(dst, points, sizeof(float) * n * 3); }))
     return 1;
   m->d_points = (float*) m->in_points.d_buf[m->in_points.which];
   m->n_points = n;
