@@ -126,6 +126,11 @@ static void free_map(mrh_map* m) {
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
   cudaFreeHost(m->h_heap_probe);
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(m->h_bounce[i]);
+    if (m->ev_bounce[i])
+      cudaEventDestroy(m->ev_bounce[i]);
+  }
   for (int i = 0; i < 8; ++i)
     if (m->ev_k[i])
       cudaEventDestroy(m->ev_k[i]);

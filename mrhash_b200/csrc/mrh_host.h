@@ -1,7 +1,9 @@
 // mrh_host.h — host-side state of one map handle (shared by the translation units of libmrhash_b200).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -11,12 +13,36 @@
 
 namespace mrh {
 
+  // Voxel payload words on the host. The allocator default-initialises (no zero fill): these vectors
+  // are hundreds of MB and every word is overwritten by the copy that follows the resize, so the
+  // memset - and taking all the page faults on one thread - would cost more than the transfer.
+  template <typename T>
+  struct NoInitAlloc : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+      using other = NoInitAlloc<U>;
+    };
+    NoInitAlloc() = default;
+    template <typename U>
+    NoInitAlloc(const NoInitAlloc<U>&) {
+    }
+    template <typename U>
+    void construct(U* p) {
+      ::new ((void*) p) U;
+    }
+    template <typename U, typename... Args>
+    void construct(U* p, Args&&... args) {
+      ::new ((void*) p) U(std::forward<Args>(args)...);
+    }
+  };
+  using VoxelWords = std::vector<uint32_t, NoInitAlloc<uint32_t>>;
+
   // Host store of streamed-out blocks: the role of Streamer::grid_ (streamer.cuh:354, the
   // unordered_map of 1 m chunks filled by integrateInChunkGrid, streamer.cpp:216-247). Records are
   // kept dense; the chunk of a record is derived on demand (worldToChunks of the block origin).
   struct HostStore {
     std::vector<GatherRecord> recs;
-    std::vector<uint32_t> voxels; // 512 x {sdf bits, sum_squared bits, rgbw} per record (reference Voxel layout)
+    VoxelWords voxels; // 512 x {sdf bits, sum_squared bits, rgbw} per record (reference Voxel layout)
     void clear() {
       recs.clear();
       voxels.clear();
@@ -30,9 +56,9 @@ namespace mrh {
 
   struct HostMesh {
     std::vector<float> triangles; // host copy of the raw soup (18 floats per triangle), fetched on demand
-    std::vector<double> vertices; // V x 3
-    std::vector<int32_t> faces;   // F x 3
-    std::vector<double> colors;   // V x 3
+    std::vector<double, NoInitAlloc<double>> vertices; // V x 3
+    std::vector<int32_t, NoInitAlloc<int32_t>> faces;  // F x 3
+    std::vector<double, NoInitAlloc<double>> colors;   // V x 3
     void clear() {
       triangles.clear(), vertices.clear(), faces.clear(), colors.clear();
     }
@@ -126,6 +152,9 @@ struct mrh_map {
   int* h_heap_probe       = nullptr; // pinned, 2 ints
   int frames_probe_seen   = -1;
   uint64_t stream_events = 0, last_stream_out = 0, last_stream_in = 0, stream_duplicates = 0;
+  // pinned bounce buffers (2 x kBounceBytes) for bulk transfers between the device and pageable host vectors
+  void* h_bounce[2]{};
+  cudaEvent_t ev_bounce[2]{};
   mrh::HostStore store;
   mrh::HostMesh mesh;
   // wall-clock breakdown of the last extractMesh (ms): stream in/out, marching-cubes kernel, device weld + D2H of the mesh, PLY
@@ -135,12 +164,16 @@ struct mrh_map {
 namespace mrh {
   int reset_map(mrh_map* m);
   // far_centre != nullptr: only blocks at least far_radius away, which also leave the device map
-  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels, const float* far_centre = nullptr, float far_radius = 0.f);
+  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, VoxelWords& voxels, const float* far_centre = nullptr, float far_radius = 0.f);
   // Streamer::stream (streamer.cpp:337-355): page far blocks out, page the host blocks around centre in
   int stream_radius(mrh_map* m, const float centre[3], float radius);
   // chunk test of Streamer::isChunkInSphere for the record's chunk (streamer.cuh:346-352)
   bool record_in_sphere(const mrh_map* m, const GatherRecord& r, const float centre[3], float radius);
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
+  // bulk copies through the pinned bounce buffers: DMA and parallel host copy overlap piece by piece
+  int bulk_d2h(mrh_map* m, void* dst_host, const void* src_dev, size_t bytes);
+  int bulk_h2d(mrh_map* m, void* dst_dev, const void* src_host, size_t bytes);
+  void parallel_copy(void* dst, const void* src, size_t bytes);
   int carve_low_blocks(mrh_map* m, uint32_t n_low);
   int weld_on_device(mrh_map* m, const float* d_soup, size_t n_tri, double eps);
   int integrate_rgbd(mrh_map* m);

@@ -213,7 +213,7 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
           // streamInToGPU(chunkToWorld(chunk), radius): chunks whose centre passes isChunkInSphere
           const float centre[3] = {(float) x * ext, (float) y * ext, (float) z * ext};
           std::vector<GatherRecord> in_recs;
-          std::vector<uint32_t> in_vox;
+          VoxelWords in_vox;
           std::vector<uint8_t> inside(st.recs.size());
           size_t n_in = 0;
           for (size_t i = 0; i < st.recs.size(); ++i) {
@@ -227,7 +227,7 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
             HostStore keep;
             for (size_t i = 0; i < st.recs.size(); ++i) {
               std::vector<GatherRecord>& rr = inside[i] ? in_recs : keep.recs;
-              std::vector<uint32_t>& vv     = inside[i] ? in_vox : keep.voxels;
+              VoxelWords& vv                = inside[i] ? in_vox : keep.voxels;
               rr.push_back(st.recs[i]);
               vv.insert(vv.end(), st.voxels.begin() + i * 3 * kBlockVoxels, st.voxels.begin() + (i + 1) * 3 * kBlockVoxels);
             }

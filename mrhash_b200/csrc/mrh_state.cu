@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   }
 
   // Gather every live block of the device map into host vectors (appended).
-  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, std::vector<uint32_t>& voxels, const float* far_centre, float far_radius) {
+  int gather_to_host(mrh_map* m, std::vector<GatherRecord>& recs, VoxelWords& voxels, const float* far_centre, float far_radius) {
     FarFilter ff{0.f, 0.f, 0.f, 0.f, 0};
     if (far_centre)
       ff = {far_centre[0], far_centre[1], far_centre[2], far_radius, 1};
@@ -260,13 +260,74 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
       if (done + got > n)
         return fail("gather_to_host: live list holds more blocks than the heap accounts for");
       CK(cudaMemcpy(recs.data() + base + done, d_recs, sizeof(GatherRecord) * got, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(voxels.data() + (base + done) * 3 * kBlockVoxels, d_vox, sizeof(uint32_t) * 3 * kBlockVoxels * got, cudaMemcpyDeviceToHost));
+      if (bulk_d2h(m, voxels.data() + (base + done) * 3 * kBlockVoxels, d_vox, sizeof(uint32_t) * 3 * kBlockVoxels * got))
+        return 1;
       done += got;
     }
     cudaFree(d_recs), cudaFree(d_vox), cudaFree(d_count);
     recs.resize(base + done);
     voxels.resize((base + done) * 3 * kBlockVoxels);
     return 0;
+  }
+
+  // ---- bulk transfers between device memory and PAGEABLE host vectors ----------------------------
+  // cudaMemcpy on pageable memory goes through the driver's own staging at a few GB/s on one thread.
+  // Here: 16 MB pieces, DMA into / out of two pinned bounce buffers, and the host side of piece k
+  // (8 threads, 256 KB slices) overlaps the DMA of piece k+1.
+  constexpr size_t kBounceBytes = 16u << 20;
+
+  void parallel_copy(void* dst, const void* src, size_t bytes) {
+    const size_t slice = 256u << 10;
+    const long n       = (long) ((bytes + slice - 1) / slice);
+    const int nthr     = (int) std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+#pragma omp parallel for num_threads(nthr) schedule(static) if (n > 2)
+    for (long i = 0; i < n; ++i) {
+      const size_t o = (size_t) i * slice;
+      memcpy((char*) dst + o, (const char*) src + o, std::min(slice, bytes - o));
+    }
+  }
+
+  static int bounce_ready(mrh_map* m) {
+    for (int i = 0; i < 2; ++i)
+      if (!m->h_bounce[i]) {
+        CK(cudaMallocHost(&m->h_bounce[i], kBounceBytes));
+        CK(cudaEventCreateWithFlags(&m->ev_bounce[i], cudaEventDisableTiming));
+      }
+    return 0;
+  }
+
+  int bulk_d2h(mrh_map* m, void* dst_host, const void* src_dev, size_t bytes) {
+    if (bounce_ready(m))
+      return 1;
+    const size_t n = (bytes + kBounceBytes - 1) / kBounceBytes;
+    for (size_t k = 0; k <= n; ++k) {
+      if (k < n) { // start the DMA of piece k
+        const size_t o = k * kBounceBytes;
+        CK(cudaMemcpyAsync(m->h_bounce[k & 1], (const char*) src_dev + o, std::min(kBounceBytes, bytes - o), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaEventRecord(m->ev_bounce[k & 1], m->stream));
+      }
+      if (k > 0) { // while it runs, move piece k-1 to its destination
+        const size_t o = (k - 1) * kBounceBytes;
+        CK(cudaEventSynchronize(m->ev_bounce[(k - 1) & 1]));
+        parallel_copy((char*) dst_host + o, m->h_bounce[(k - 1) & 1], std::min(kBounceBytes, bytes - o));
+      }
+    }
+    return 0;
+  }
+
+  int bulk_h2d(mrh_map* m, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bounce_ready(m))
+      return 1;
+    const size_t n = (bytes + kBounceBytes - 1) / kBounceBytes;
+    for (size_t k = 0; k < n; ++k) {
+      const size_t o = k * kBounceBytes, len = std::min(kBounceBytes, bytes - o);
+      if (k >= 2)
+        CK(cudaEventSynchronize(m->ev_bounce[k & 1])); // the DMA that last read this buffer has finished
+      parallel_copy(m->h_bounce[k & 1], (const char*) src_host + o, len);
+      CK(cudaMemcpyAsync((char*) dst_dev + o, m->h_bounce[k & 1], len, cudaMemcpyHostToDevice, m->stream));
+      CK(cudaEventRecord(m->ev_bounce[k & 1], m->stream));
+    }
+    return 0; // the caller's next stream operation (or synchronise) orders after the copies
   }
 
   // one pass: records with pairwise different keys
@@ -279,7 +340,8 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     for (size_t first = 0; first < n; first += chunk) {
       const size_t k = std::min(chunk, n - first);
       CK(cudaMemcpyAsync(d_recs, recs + first, sizeof(GatherRecord) * k, cudaMemcpyHostToDevice, m->stream));
-      CK(cudaMemcpyAsync(d_vox, voxels + first * 3 * kBlockVoxels, sizeof(uint32_t) * 3 * kBlockVoxels * k, cudaMemcpyHostToDevice, m->stream));
+      if (bulk_h2d(m, d_vox, voxels + first * 3 * kBlockVoxels, sizeof(uint32_t) * 3 * kBlockVoxels * k))
+        return 1;
       k_insert_blocks<<<m->num_sms * 8, 128, 0, m->stream>>>(m->dev, m->live_cur, d_recs, d_vox, (uint32_t) k);
       m->launches++;
       CK(cudaStreamSynchronize(m->stream));
@@ -313,7 +375,7 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     const size_t words = (size_t) 3 * kBlockVoxels;
     for (uint32_t p = 0; p < n_pass; ++p) {
       std::vector<GatherRecord> r;
-      std::vector<uint32_t> v;
+      VoxelWords v;
       for (size_t i = 0; i < n; ++i)
         if (pass[i] == p) {
           r.push_back(recs[i]);
@@ -352,12 +414,12 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
     m->last_stream_out = st.recs.size() - before;
     // stream in (streamInToGPU / integrateInHash): every stored block whose chunk lies in the sphere
     std::vector<GatherRecord> in_recs, keep_recs;
-    std::vector<uint32_t> in_vox, keep_vox;
+    VoxelWords in_vox, keep_vox;
     const size_t words = (size_t) 3 * kBlockVoxels;
     for (size_t i = 0; i < st.recs.size(); ++i) {
       const bool in = i < before && record_in_sphere(m, st.recs[i], centre, radius); // what just left stays out
       (in ? in_recs : keep_recs).push_back(st.recs[i]);
-      std::vector<uint32_t>& vv = in ? in_vox : keep_vox;
+      VoxelWords& vv = in ? in_vox : keep_vox;
       vv.insert(vv.end(), st.voxels.begin() + i * words, st.voxels.begin() + (i + 1) * words);
     }
     m->last_stream_in = in_recs.size();
@@ -391,7 +453,7 @@ int mrh_dump_state(mrh_map* m, mrh_dump_entry* entries, void* voxels, size_t max
     return fail("null argument");
   CK(cudaSetDevice(m->device));
   std::vector<GatherRecord> recs;
-  std::vector<uint32_t> vox;
+  VoxelWords vox;
   if (gather_to_host(m, recs, vox))
     return 1;
   *n_out = recs.size();
@@ -501,7 +563,8 @@ int mrh_serialize_data(mrh_map* m, const char* hash_path, const char* voxel_path
   }
   const uint64_t n_vox = vofs[nrec], n_hash = hofs[nrec];
   // records: voxel point = x,y,z,sdf,weight,rgba (24 B); hash point = x,y,z,weight,rgba (20 B)
-  std::vector<uint8_t> vbuf(n_vox * 24), hbuf(n_hash * 20);
+  // every byte is written by the parallel fill below: no zero fill of the (GB-sized) buffers
+  std::vector<uint8_t, NoInitAlloc<uint8_t>> vbuf(n_vox * 24), hbuf(n_hash * 20);
   parallel([&](size_t k) {
     if (!count[k + 1])
       return;
@@ -541,7 +604,7 @@ int mrh_serialize_data(mrh_map* m, const char* hash_path, const char* voxel_path
     memcpy(hp + 12, &avg_w, 4);
     memcpy(hp + 16, hc, 4);
   });
-  auto write_ply = [&](const char* path, uint64_t n, bool with_sdf, const std::vector<uint8_t>& data) -> int {
+  auto write_ply = [&](const char* path, uint64_t n, bool with_sdf, const std::vector<uint8_t, NoInitAlloc<uint8_t>>& data) -> int {
     if (n == 0) {
       fprintf(stderr, "PointCloudSerializer|empty point cloud\n");
       return 0;

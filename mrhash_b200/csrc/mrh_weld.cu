@@ -241,10 +241,9 @@ namespace mrh {
     m->launches += 1;
     CK(cudaGetLastError());
     mesh.vertices.resize(3ull * n_unique), mesh.colors.resize(3ull * n_unique), mesh.faces.resize(3ull * n_faces);
-    CK(cudaMemcpyAsync(mesh.vertices.data(), dV.p, 24ull * n_unique, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(mesh.colors.data(), dC.p, 24ull * n_unique, cudaMemcpyDeviceToHost, s));
-    if (n_faces)
-      CK(cudaMemcpyAsync(mesh.faces.data(), dF.p, 12ull * n_faces, cudaMemcpyDeviceToHost, s));
+    // pageable destinations: pinned bounce buffers, DMA overlapped with a parallel host copy (mrh_state.cu)
+    if (bulk_d2h(m, mesh.vertices.data(), dV.p, 24ull * n_unique) || bulk_d2h(m, mesh.colors.data(), dC.p, 24ull * n_unique) || (n_faces && bulk_d2h(m, mesh.faces.data(), dF.p, 12ull * n_faces)))
+      return 1;
     CK(cudaStreamSynchronize(s));
     return 0;
   }
