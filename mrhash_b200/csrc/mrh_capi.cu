@@ -193,7 +193,8 @@ static void staged_copy(void* dst, const void* src, size_t bytes) {
     memcpy(dst, src, bytes);
     return;
   }
-#pragma omp parallel for num_threads(copy_threads()) schedule(static)
+  const int nthr = copy_threads();
+#pragma omp parallel for num_threads(nthr) schedule(static)
   for (long i = 0; i < n; ++i) {
     const size_t o = (size_t) i * slice;
     memcpy((char*) dst + o, (const char*) src + o, std::min(slice, bytes - o));
@@ -447,7 +448,8 @@ int mrh_set_rgb_f32(mrh_map* m, const float* rgb, int rows, int cols) {
     return fail("GeoWrapper::setRGBImage|input should be a 3D numpy array");
   const size_t n = (size_t) rows * cols * 3;
   if (ingest_upload<uint8_t>(m, m->in_rgb, nullptr, n, [&](uint8_t* dst) {
-#pragma omp parallel for num_threads(copy_threads()) schedule(static)
+        const int nthr = copy_threads();
+#pragma omp parallel for num_threads(nthr) schedule(static)
         for (long i = 0; i < (long) n; ++i)
           dst[i] = (uint8_t) rgb[i];
       }))
