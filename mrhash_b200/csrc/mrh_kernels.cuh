@@ -178,8 +178,11 @@ __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uin
 // ---------------------------------------------------------------------------------------------
 // rearm: the last CTA to finish zeroes the list counters the next frame's k_front appends to (every
 // CTA has read vis_count by then), so a frame needs no reset kernel.
+#ifndef MRH_INTEGRATE_MIN_CTAS
+#define MRH_INTEGRATE_MIN_CTAS 1 // tuning knob: forces a register budget for more resident CTAs
+#endif
 template <bool FUSE_GC>
-__global__ void __launch_bounds__(128) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
+__global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
   __shared__ float s_min[4];
   __shared__ uint32_t s_max[4];
   __shared__ uint32_t s_upd[4];

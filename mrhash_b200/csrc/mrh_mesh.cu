@@ -87,7 +87,7 @@ namespace {
         *p++ = ' ';
       }
       for (int k = 0; k < 3; ++k) {
-        p += fmt_uint((uint32_t) (unsigned char) C[3 * i + k], p);
+        p += fmt_uint((uint32_t) (unsigned char) (long long) C[3 * i + k], p); // via an integer: double -> uchar out of range is undefined
         *p++ = k == 2 ? '\n' : ' ';
       }
       return (size_t) (p - dst);
