@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from conftest import ROOT
 
@@ -61,3 +62,35 @@ def test_bench_reference_arm_reports_unavailable_without_gpu():
 
     if not torch.cuda.is_available():
         assert "unavailable" in line
+
+
+def test_reference_config_surface(tmp_path):
+    """configurations/*.cfg of the reference (YAML) -> GeoWrapper keywords (mrhash_b200/config.py)."""
+    import inspect
+
+    from mrhash_b200 import GeoWrapper, synth
+    from mrhash_b200.config import load_config
+
+    cfg = tmp_path / "replica.cfg"
+    cfg.write_text(
+        "map:\n    sdf_truncation            : 0.07\n    sdf_truncation_scale      : 0.00\n    integration_weight_sample : 1 \n"
+        "    virtual_voxel_size        : 0.01\n    n_frames_invalidate_voxels: 100\n\nstreamer:\n    voxel_extents_scale       : 1\n\n"
+        "mesh:\n    marching_cubes_threshold: 1.5\n    min_weight_threshold : 5\n    sdf_var_threshold : 0.0\n    vertices_merging_threshold : 0.0\n\n"
+        "sensor:\n    min_depth : 0.01\n    max_depth : 30\n    intrinsics: [600.0, 600.0, 599.5, 339.5]\n    resolution: [1200, 680]\n"
+        "    depth_scaling: 6553.5\n    hz: 30\n\ndata_path: /data\nresults_path: /out\ngs_optimization_param_path: ./params.json\nend_frame: -1\n"
+    )
+    kw, sensor = load_config(str(cfg))
+    # the same values as the hard-coded replica parameters the tests use, and only constructor keywords
+    for k, v in synth.REPLICA_PARAMS.items():
+        assert kw[k] == pytest.approx(v), k
+    accepted = set(inspect.signature(GeoWrapper.__init__).parameters)
+    assert set(kw) <= accepted
+    assert sensor["resolution"] == [1200, 680] and sensor["end_frame"] == -1 and sensor["depth_scaling"] == 6553.5
+    lidar = {"map": {"sdf_truncation": 0.4, "sdf_truncation_scale": 0.0, "integration_weight_sample": 1, "virtual_voxel_size": 0.2, "n_frames_invalidate_voxels": 0},
+             "streamer": {"voxel_extents_scale": 1}, "mesh": {"marching_cubes_threshold": 1.5, "sdf_var_threshold": 0.0, "vertices_merging_threshold": 0.0, "min_weight_threshold": 50},
+             "sensor": {"min_depth": 0.2, "max_depth": 100, "rosbag_topic": "/ouster/points"}, "end_frame": -1}
+    kw, sensor = load_config(lidar)
+    for k, v in synth.VBR_PARAMS.items():
+        assert kw[k] == pytest.approx(v), k
+    with pytest.raises(KeyError, match="mesh"):
+        load_config({"map": lidar["map"], "streamer": lidar["streamer"], "sensor": lidar["sensor"]})
