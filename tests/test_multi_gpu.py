@@ -329,3 +329,33 @@ def test_starve_frames_min_reduce_the_zbuffer_across_shards():
     rep_no, _ = run(False)
     print("[starve, no reduction]", {k: rep_no[k] for k in ("only_a", "only_b", "weight_mismatch")})
     assert rep_no["weight_mismatch"] > 10 * max(1, rep["weight_mismatch"])  # the reduction is what makes it right
+
+
+def test_lidar_shards_union_equals_unsharded_map():
+    """The point-cloud path shards the same way (allocBlocks3D / integrate3D touch only owned blocks):
+    three shard handles fed the same clouds hold, together, exactly the unsharded map."""
+    p = dict(synth.VBR_PARAMS)
+    rows, cols = synth.LIDAR_ROWS, synth.LIDAR_COLS
+    K = (-cols / (2 * np.pi), -rows / (np.pi / 2), cols / 2, rows / 2)
+
+    def mk(rank, n):
+        g = GeoWrapper(**p, num_sdf_blocks=120000, hash_num_buckets=60000, max_num_triangles=1, shard_rank=rank, shard_world=n)
+        g.setCamera(*K, rows, cols, p["min_depth"], p["max_depth"], 1)
+        return g
+
+    whole, shards = mk(0, 1), [mk(r, 3) for r in range(3)]
+    for k in range(3):
+        T, pts = synth.lidar_frame(k, noise_sigma=0.01)
+        for g in [whole] + shards:
+            g.setCurrPoseMatrix(T)
+            g.setPointCloud(pts, False)
+            g.compute()
+    parts = [g.dumpState() for g in shards]
+    for r, (e, _) in enumerate(parts):
+        assert len(e) > 500 and (sharding.owner_of(e[:, :3], 3, 60000) == r).all()
+    ee = np.concatenate([e for e, _ in parts])
+    vv = np.concatenate([v for _, v in parts])
+    order = np.lexsort((ee[:, 2], ee[:, 1], ee[:, 0]))
+    rep = compare_dumps((ee[order], vv[order]), whole.dumpState())
+    assert rep["ok"] and rep["sdf_bitexact"] and rep["sum_squared_bitexact"], rep
+    assert sum(g.getStats()["voxels_updated"] for g in shards) == whole.getStats()["voxels_updated"]
