@@ -193,6 +193,9 @@ int mrh_deserialize_grid(mrh_map* m, const char* path);
  * voxels per record (a resolution-1 record uses the first 64) */
 int mrh_grid_write(const char* path, const mrh_dump_entry* entries, const void* voxels, size_t n, float virtual_voxel_size, float voxel_extents);
 int mrh_grid_read(const char* path, mrh_dump_entry* entries, void* voxels, size_t max_entries, size_t* n_out);
+/* test hook: the number formatter of the ASCII PLY writer (`ostream << double` of geowrapper.cpp:194-229,
+ * i.e. printf("%g")); writes at most 32 bytes, no terminator, returns the length */
+size_t mrh_format_g6(double v, char* dst);
 /* GeoWrapper::clearBuffers (geowrapper.cpp:552-557) */
 int mrh_clear_buffers(mrh_map* m);
 

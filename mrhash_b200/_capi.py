@@ -106,6 +106,7 @@ SIGNATURES = {
     "mrh_deserialize_grid": ([_vp, C.c_char_p], _i),
     "mrh_grid_write": ([C.c_char_p, _vp, _vp, C.c_size_t, _f, _f], _i),
     "mrh_grid_read": ([C.c_char_p, _vp, _vp, C.c_size_t, _P(C.c_size_t)], _i),
+    "mrh_format_g6": ([C.c_double, C.c_char_p], C.c_size_t),
     "mrh_clear_buffers": ([_vp], _i),
     "mrh_get_field": ([_vp, C.c_char_p, _P(C.c_double)], _i),
     "mrh_set_field": ([_vp, C.c_char_p, C.c_double], _i),

@@ -20,6 +20,7 @@
 #include <map>
 #include <vector>
 
+#include "mrh_fmt.h"
 #include "mrh_host.h"
 
 using namespace mrh;
@@ -174,6 +175,10 @@ namespace {
 } // namespace
 
 extern "C" {
+
+size_t mrh_format_g6(double v, char* dst) {
+  return fmt_g6(v, dst);
+}
 
 int mrh_grid_write(const char* path, const mrh_dump_entry* entries, const void* voxels, size_t n, float virtual_voxel_size, float voxel_extents) {
   if (!path || (n && (!entries || !voxels)))

@@ -103,3 +103,32 @@ def test_cista_itself_reads_what_the_writer_produces(tmp_path):
         off += 12 * nv
     want = {k: (a, b[: 12 * (512 if a[0] == 0 else 64)]) for k, (a, b) in by_key(entries, voxels).items()}
     assert seen == want
+
+
+def test_ply_number_formatter_equals_printf_g():
+    """csrc/mrh_fmt.h (the ASCII PLY writer's fast path) against printf's %g on floats widened to double:
+    random bit patterns, the mesh's usual range, decade edges and decimal ties."""
+    import ctypes as C
+
+    from mrhash_b200 import _capi
+
+    lib = _capi.lib()
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(9)
+    vals = [rng.integers(0, 2**32, 60000, dtype=np.uint64).astype(np.uint32).view(np.float32), (rng.random(60000) * 20 - 10).astype(np.float32),
+            (rng.random(20000) * 2e-3 - 1e-3).astype(np.float32), (rng.random(20000) * 2e6 - 1e6).astype(np.float32),
+            np.array([0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 1e-4, 9.99999e-5, 1e-5, 0.001, 0.1, 1, 10, 100000, 999999, 999999.5, 1e6, 123456.5, 12345.65, 1.0000005, 9.999995, 99999.95, 262144.5], np.float32)]
+    vals.append(np.nextafter(vals[-1], np.float32(1e9)))
+    vals.append(np.nextafter(vals[-2], np.float32(-1e9)))
+    n = 0
+    for arr in vals:
+        with np.errstate(invalid="ignore"):  # signalling NaN bit patterns among the random floats
+            wide = arr.astype(np.float64).tolist()
+        for v in wide:
+            if not np.isfinite(v):
+                continue
+            for x in (v, -v):
+                k = lib.mrh_format_g6(x, buf)
+                assert buf.raw[:k].decode() == "%g" % x, x
+                n += 1
+    assert n > 300000
