@@ -1,6 +1,8 @@
 /* mrhash_b200.h — C ABI of libmrhash_b200.so, the B200-native drop-in for mrhash's
  * GeoWrapper::compute() hot path (depth-ray block allocation into the spatial hash, TSDF fusion,
- * garbage collection, variance-adaptive re-allocation) plus extractMesh() and serializeData().
+ * garbage collection, variance-adaptive re-allocation, LiDAR point clouds, radius paging) plus
+ * extractMesh(), serializeData(), serializeGrid() and the multi-GPU support calls (sharded starve
+ * frames, boundary exchange for meshing).
  *
  * The reference has no C ABI: its boundary is the nanobind class `pygeowrapper.GeoWrapper`
  * (/root/reference/mrhash/src/sdf/pybind/pygeowrapper.cpp:12-84) over the C++ class
