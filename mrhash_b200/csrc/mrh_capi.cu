@@ -310,7 +310,7 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   m->num_sms = prop.multiProcessorCount;
   {
     const char* e      = getenv("MRH_INTEGRATE_CTAS_PER_SM");
-    const int per_sm   = e ? std::max(1, atoi(e)) : 9;
+    const int per_sm   = e ? std::max(1, atoi(e)) : integrate_ctas_per_sm(); // one wave of resident CTAs
     m->integrate_grid = m->num_sms * per_sm;
   }
 

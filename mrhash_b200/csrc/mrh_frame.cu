@@ -24,6 +24,10 @@ namespace mrh {
       return fail("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_));               \
   } while (0)
 
+int integrate_ctas_per_sm() {
+  return kIntVox == 2 ? 6 : 9;
+}
+
 FrameDev make_frame(const mrh_map* m) {
   FrameDev f;
   for (int i = 0; i < 3; ++i) {
@@ -206,9 +210,9 @@ int integrate_rgbd(mrh_map* m) {
       cudaStreamWaitEvent(s, m->rgb_ready, 0);
     mark(2);
     if (fused_gc)
-      k_integrate<true><<<m->integrate_grid, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      k_integrate<true><<<m->integrate_grid, kIntThreads, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     else
-      k_integrate<false><<<m->integrate_grid, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      k_integrate<false><<<m->integrate_grid, kIntThreads, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     CKL();
     mark(3);
     m->launches += 2;
@@ -226,7 +230,7 @@ int integrate_rgbd(mrh_map* m) {
     if (m->rgb_ready)
       cudaStreamWaitEvent(s, m->rgb_ready, 0);
     mark(2);
-    k_integrate<false><<<c.grid_blocks, 128, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, 0);
+    k_integrate<false><<<c.grid_blocks, kIntThreads, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, 0);
     CKL();
     mark(3);
     m->launches += 3;

@@ -180,4 +180,5 @@ namespace mrh {
   int integrate_points(mrh_map* m);
   int finish_gc_tail(mrh_map* m);
   FrameDev make_frame(const mrh_map* m);
+  int integrate_ctas_per_sm(); // resident CTAs per SM of k_integrate as compiled (mrh_frame.cu)
 } // namespace mrh

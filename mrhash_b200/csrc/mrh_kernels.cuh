@@ -178,19 +178,43 @@ __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uin
 // ---------------------------------------------------------------------------------------------
 // rearm: the last CTA to finish zeroes the list counters the next frame's k_front appends to (every
 // CTA has read vis_count by then), so a frame needs no reset kernel.
-#ifndef MRH_INTEGRATE_MIN_CTAS
-#define MRH_INTEGRATE_MIN_CTAS 1 // tuning knob: forces a register budget for more resident CTAs
+// Consecutive-x voxels per thread: 2 (256 threads per block, 64-bit plane access) with a 40-register
+// budget keeps 48 warps per SM resident; 4 (128 threads, 128-bit access, 56 registers) only 36. The
+// kernel is latency-bound, so the extra warps win: 45.4 vs 47.4 us per frame (profiles/r1_summary.md).
+#ifndef MRH_INTEGRATE_VOX
+#define MRH_INTEGRATE_VOX 2
 #endif
+#ifndef MRH_INTEGRATE_MIN_CTAS
+#define MRH_INTEGRATE_MIN_CTAS (MRH_INTEGRATE_VOX == 2 ? 6 : 1) // resident CTAs per SM the register budget must allow
+#endif
+constexpr int kIntVox     = MRH_INTEGRATE_VOX;
+constexpr int kIntThreads = kBlockVoxels / kIntVox;
+constexpr int kIntWarps   = kIntThreads / 32;
+template <int V>
+struct PlaneVec;
+template <>
+struct PlaneVec<4> {
+  using F = float4;
+  using U = uint4;
+};
+template <>
+struct PlaneVec<2> {
+  using F = float2;
+  using U = uint2;
+};
 template <bool FUSE_GC>
-__global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
-  __shared__ float s_min[4];
-  __shared__ uint32_t s_max[4];
-  __shared__ uint32_t s_upd[4];
+__global__ void __launch_bounds__(kIntThreads, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int rearm) {
+  using VF = typename PlaneVec<kIntVox>::F;
+  using VU = typename PlaneVec<kIntVox>::U;
+  __shared__ float s_min[kIntWarps];
+  __shared__ uint32_t s_max[kIntWarps];
+  __shared__ uint32_t s_upd[kIntWarps];
   __shared__ int s_delete;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PoseDev& pose  = frame_pose(f);
   const uint32_t n_vis = m.ctr->vis_count;
-  const int lx0 = (tid & 1) * 4, ly = (tid >> 1) & 7, lz = tid >> 4;
+  constexpr int kPerRow = kBlockSide / kIntVox; // threads per row of 8 voxels
+  const int lx0 = (tid % kPerRow) * kIntVox, ly = (tid / kPerRow) & 7, lz = tid / (kPerRow * 8);
   const float half_size = fmul(m.voxel_size, 0.5f);
   unsigned long long cta_updated = 0;
   for (uint32_t bi = blockIdx.x; bi < n_vis; bi += gridDim.x) {
@@ -198,21 +222,21 @@ __global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDe
     if (e.val & 0x80000000u)
       continue; // resolution-1 blocks are fused by k_integrate_lowres
     uint8_t* base = m.pool + (size_t) e.val * kBlockBytes;
-    if (e.maybe_in_image && (tid & 7) == 0) {
+    if (e.maybe_in_image && (tid % (32 / kIntVox)) == 0) {
       // the three planes are read after the projection pass: start moving their lines (one per 8
       // threads) towards L2 now, the projection and the depth gathers hide the DRAM latency
-      prefetch_l2(base + 16 * tid);
-      prefetch_l2(base + kPlaneBytes + 16 * tid);
-      prefetch_l2(base + 2 * kPlaneBytes + 16 * tid);
+      prefetch_l2(base + 4 * kIntVox * tid);
+      prefetch_l2(base + kPlaneBytes + 4 * kIntVox * tid);
+      prefetch_l2(base + 2 * kPlaneBytes + 4 * kIntVox * tid);
     }
     // ---- pass 1: projection + depth test, registers only ----
-    float sdf_new[4] = {0.f, 0.f, 0.f, 0.f};
-    uint32_t pix[4]  = {0u, 0u, 0u, 0u};
+    float sdf_new[kIntVox] = {};
+    uint32_t pix[kIntVox]  = {};
     unsigned ok      = 0;
     if (e.maybe_in_image) { // else: no voxel of this block can project into the image (k_visible)
     const f3 pf_yz = {0.f, fmul(i2f(e.y * kBlockSide + ly), m.voxel_size), fmul(i2f(e.z * kBlockSide + lz), m.voxel_size)};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kIntVox; ++j) {
       const f3 pf = {fmul(i2f(e.x * kBlockSide + lx0 + j), m.voxel_size), pf_yz.y, pf_yz.z};
       const f3 pc = se3_mul(pose.Ri, pose.ti, pf);
       int row, col;
@@ -235,18 +259,18 @@ __global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDe
     const int any = e.maybe_in_image ? __syncthreads_or((int) ok) : 0;
     float min_abs  = 3.40282346638528859812e+38f;
     uint32_t max_w = 0, n_upd = 0;
-    float4 sdf4, ss4;
-    uint4 cw4;
+    VF sdf4, ss4;
+    VU cw4;
     if (any) {
       // ---- pass 2: 128-bit loads of this thread's 4 voxels from the three planes ----
-      sdf4 = reinterpret_cast<const float4*>(base)[tid];
-      ss4  = reinterpret_cast<const float4*>(base + kPlaneBytes)[tid];
-      cw4  = reinterpret_cast<const uint4*>(base + 2 * kPlaneBytes)[tid];
+      sdf4 = reinterpret_cast<const VF*>(base)[tid];
+      ss4  = reinterpret_cast<const VF*>(base + kPlaneBytes)[tid];
+      cw4  = reinterpret_cast<const VU*>(base + 2 * kPlaneBytes)[tid];
       float* sdfv    = reinterpret_cast<float*>(&sdf4);
       float* ssv     = reinterpret_cast<float*>(&ss4);
       uint32_t* cwv  = reinterpret_cast<uint32_t*>(&cw4);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kIntVox; ++j) {
         if (ok & (1u << j)) {
           // integrateDepthMapKernel :1155-1180 + combineVoxel (voxel_hash_utils.cuh:169-181)
           const uint32_t cw = cwv[j];
@@ -293,9 +317,15 @@ __global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDe
     if (tid == 0) {
       BlockStats st;
       if (any) {
-        st.min_abs_sdf = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3]));
-        st.max_weight  = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
-        cta_updated += s_upd[0] + s_upd[1] + s_upd[2] + s_upd[3];
+        st.min_abs_sdf = s_min[0], st.max_weight = s_max[0];
+        uint32_t upd   = s_upd[0];
+#pragma unroll
+        for (int w = 1; w < kIntWarps; ++w) {
+          st.min_abs_sdf = fminf(st.min_abs_sdf, s_min[w]);
+          st.max_weight  = max(st.max_weight, s_max[w]);
+          upd += s_upd[w];
+        }
+        cta_updated += upd;
       } else {
         st = m.stats[e.val];
       }
@@ -317,14 +347,15 @@ __global__ void __launch_bounds__(128, MRH_INTEGRATE_MIN_CTAS) k_integrate(MapDe
     const int del = FUSE_GC ? s_delete : 0;
     if (del) {
       // deleteVoxel over the whole block (:1838-1841): free pool blocks are always all-zero
-      const float4 z = {0.f, 0.f, 0.f, 0.f};
-      reinterpret_cast<float4*>(base)[tid]                   = z;
-      reinterpret_cast<float4*>(base + kPlaneBytes)[tid]     = z;
-      reinterpret_cast<float4*>(base + 2 * kPlaneBytes)[tid] = z;
+      VF z;
+      memset(&z, 0, sizeof(z));
+      reinterpret_cast<VF*>(base)[tid]                   = z;
+      reinterpret_cast<VF*>(base + kPlaneBytes)[tid]     = z;
+      reinterpret_cast<VF*>(base + 2 * kPlaneBytes)[tid] = z;
     } else if (ok) {
-      reinterpret_cast<float4*>(base)[tid]                  = sdf4;
-      reinterpret_cast<float4*>(base + kPlaneBytes)[tid]    = ss4;
-      reinterpret_cast<uint4*>(base + 2 * kPlaneBytes)[tid] = cw4;
+      reinterpret_cast<VF*>(base)[tid]                   = sdf4;
+      reinterpret_cast<VF*>(base + kPlaneBytes)[tid]     = ss4;
+      reinterpret_cast<VU*>(base + 2 * kPlaneBytes)[tid] = cw4;
     }
     __syncthreads(); // s_* reused by the next block of this CTA
   }
