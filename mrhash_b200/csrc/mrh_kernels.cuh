@@ -174,7 +174,7 @@ __device__ __forceinline__ bool gc_predicate(const MapDev& m, float min_abs, uin
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_integrate: one CTA (128 threads x 4 consecutive-x voxels) per visible block, persistent.
+// k_integrate: one CTA (kIntThreads threads x kIntVox consecutive-x voxels) per visible block, persistent.
 // ---------------------------------------------------------------------------------------------
 // rearm: the last CTA to finish zeroes the list counters the next frame's k_front appends to (every
 // CTA has read vis_count by then), so a frame needs no reset kernel.
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kIntThreads, MRH_INTEGRATE_MIN_CTAS) k_integra
     VF sdf4, ss4;
     VU cw4;
     if (any) {
-      // ---- pass 2: 128-bit loads of this thread's 4 voxels from the three planes ----
+      // ---- pass 2: vector loads of this thread's voxels from the three planes ----
       sdf4 = reinterpret_cast<const VF*>(base)[tid];
       ss4  = reinterpret_cast<const VF*>(base + kPlaneBytes)[tid];
       cw4  = reinterpret_cast<const VU*>(base + 2 * kPlaneBytes)[tid];
