@@ -308,6 +308,8 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   m->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("MRH_PDL"))
+    m->use_pdl = atoi(e) != 0;
   {
     const char* e      = getenv("MRH_INTEGRATE_CTAS_PER_SM");
     const int per_sm   = e ? std::max(1, atoi(e)) : integrate_ctas_per_sm(); // one wave of resident CTAs

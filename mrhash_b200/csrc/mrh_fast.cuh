@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(kFrontThreads, MRH_FRONT_MIN_CTAS * 8 / MRH_FR
   __shared__ unsigned long long s_list[kTileSet];
   __shared__ uint32_t s_n;
   __shared__ int s_full;
+  cudaGridDependencySynchronize(); // chained launch: the previous frame's k_integrate has completed (no-op otherwise)
   const PoseDev& pose = frame_pose(f);
   if (blockIdx.x < n_vis_ctas) { // scheduled first: the visibility role is a pure latency chain
     visible_pass(m, f.live_cur, cam, pose, 1, blockIdx.x, n_vis_ctas);

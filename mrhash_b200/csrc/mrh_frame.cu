@@ -6,6 +6,7 @@
 // (its sort runs over a record count the host knows in advance).
 #include <algorithm>
 #include <cmath>
+#include <utility>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -55,6 +56,25 @@ FrameDev make_frame(const mrh_map* m) {
 }
 
 namespace {
+
+  // Launch with programmatic stream serialisation (programmatic dependent launch): the grid is staged
+  // while the previous kernel of the stream drains, and its CTAs block in cudaGridDependencySynchronize()
+  // (first statement of k_front / k_integrate) until that kernel has completed and flushed - the launch
+  // latency between the two kernels of a frame, and between frames, disappears from the critical path.
+  template <typename... KArgs, typename... Args>
+  cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool chained, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = block;
+    cfg.dynamicSmemBytes   = 0;
+    cfg.stream             = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  }
 
   struct FrameCtx {
     mrh_map* m;
@@ -203,16 +223,16 @@ int integrate_rgbd(mrh_map* m) {
     const uint32_t n_vis_ctas = (uint32_t) m->num_sms;
     const int rearm           = c.starve ? 0 : 1;
     mark(0);
-    k_front<<<tiles_x * tiles_y + n_vis_ctas, kFrontThreads, 0, s>>>(d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
+    launch_chained(k_front, dim3(tiles_x * tiles_y + n_vis_ctas), dim3(kFrontThreads), s, m->use_pdl && m->counters_clean, d, f, k, m->depth_ptr, tiles_x, n_vis_ctas);
     CKL();
     mark(1);
     if (m->rgb_ready)
       cudaStreamWaitEvent(s, m->rgb_ready, 0);
     mark(2);
     if (fused_gc)
-      k_integrate<true><<<m->integrate_grid, kIntThreads, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      launch_chained(k_integrate<true>, dim3(m->integrate_grid), dim3(kIntThreads), s, m->use_pdl, d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     else
-      k_integrate<false><<<m->integrate_grid, kIntThreads, 0, s>>>(d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
+      launch_chained(k_integrate<false>, dim3(m->integrate_grid), dim3(kIntThreads), s, m->use_pdl, d, f, k, m->depth_ptr, m->rgb_ptr, rearm);
     CKL();
     mark(3);
     m->launches += 2;

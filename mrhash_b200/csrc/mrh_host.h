@@ -114,6 +114,7 @@ struct mrh_map {
 
   uint32_t frame_index = 0; // num_integrated_frames_ (voxel_data_structures.cpp:106)
   uint32_t live_cur    = 0;
+  bool use_pdl         = true; // programmatic dependent launch of the two frame kernels (env MRH_PDL=0 switches it off)
   bool counters_clean  = true; // live_count[live_cur ^ 1] and vis_count are already zero (fast RGB-D path precondition)
   uint64_t frames_total = 0;
   uint64_t launches     = 0;

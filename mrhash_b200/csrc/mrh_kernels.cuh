@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kIntThreads, MRH_INTEGRATE_MIN_CTAS) k_integra
   __shared__ uint32_t s_upd[kIntWarps];
   __shared__ int s_delete;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cudaGridDependencySynchronize(); // chained launch: k_front has completed and its lists are visible (no-op otherwise)
   const PoseDev& pose  = frame_pose(f);
   const uint32_t n_vis = m.ctr->vis_count;
   constexpr int kPerRow = kBlockSide / kIntVox; // threads per row of 8 voxels
