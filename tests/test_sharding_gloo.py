@@ -128,6 +128,32 @@ def _halo_worker(rank, world, port, out):
             else:
                 assert rec[0] == -1
         assert n_found > 0
+        # starve frames: compute_sharded min-reduces the z-buffer between computeBegin and computeEnd
+        class _Starve:
+            def __init__(self, starve):
+                self.starve, self.log = starve, []
+                self.z = torch.full((16,), 0x7F7F7F7F7F7F7F7F, dtype=torch.int64)
+                self.z[rank::world] = torch.arange(len(self.z[rank::world]), dtype=torch.int64) + 10 * (rank + 1)
+
+            def computeBegin(self):
+                self.log.append("begin")
+                return self.starve
+
+            def zbufTensor(self):
+                return self.z
+
+            def computeEnd(self):
+                self.log.append("end")
+
+        s0 = _Starve(False)
+        assert sharding.compute_sharded(s0) is False and s0.log == ["begin", "end"]
+        s1 = _Starve(True)
+        assert sharding.compute_sharded(s1) is True and s1.log == ["begin", "end"]
+        want = torch.full((16,), 0x7F7F7F7F7F7F7F7F, dtype=torch.int64)
+        for r in range(world):
+            n = len(want[r::world])
+            want[r::world] = torch.arange(n, dtype=torch.int64) + 10 * (r + 1)
+        assert torch.equal(s1.z, want)  # every rank holds the per-cell minimum over the ranks
         # owner_of_torch == owner_of
         assert np.array_equal(sharding.owner_of_torch(torch.from_numpy(blocks), world, nb).numpy(), sharding.owner_of(blocks, world, nb))
         out.put((rank, "ok"))
