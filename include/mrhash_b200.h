@@ -154,6 +154,9 @@ int mrh_extract_mesh(mrh_map* m, const char* path_or_null);
 int mrh_extract_mesh_ex(mrh_map* m, const char* path_or_null, int force_generic);
 /* GeoWrapper::getVertices / getFaces / getColors (geowrapper.h:91-93); pointers stay valid until the next extract */
 int mrh_get_mesh(mrh_map* m, const double** vertices, const int32_t** faces, const double** colors, size_t* n_vertices, size_t* n_faces);
+/* the ASCII PLY writer of extractMesh (geowrapper.cpp:194-229) on caller-supplied arrays (no handle, no device:
+ * tooling and the CPU test of the file format) */
+int mrh_write_mesh_ply(const char* path, const double* vertices, const double* colors, const int32_t* faces, size_t n_vertices, size_t n_faces);
 /* raw triangle soup of the last extract (72-byte Triangle records, voxel_hash_utils.cuh:46-64) */
 int mrh_get_triangles(mrh_map* m, const float** triangles, size_t* n_triangles);
 /* ---- sharded meshing (no reference counterpart: the reference is single-GPU; marching_cubes.cu:72-214

@@ -101,6 +101,7 @@ SIGNATURES = {
     "mrh_extract_mesh_ex": ([_vp, C.c_char_p, _i], _i),
     "mrh_get_mesh": ([_vp, _P(_P(C.c_double)), _P(_P(C.c_int32)), _P(_P(C.c_double)), _P(C.c_size_t), _P(C.c_size_t)], _i),
     "mrh_get_triangles": ([_vp, _P(_fp), _P(C.c_size_t)], _i),
+    "mrh_write_mesh_ply": ([C.c_char_p, _vp, _vp, _vp, C.c_size_t, C.c_size_t], _i),
     "mrh_serialize_data": ([_vp, C.c_char_p, C.c_char_p], _i),
     "mrh_serialize_grid": ([_vp, C.c_char_p], _i),
     "mrh_deserialize_grid": ([_vp, C.c_char_p], _i),

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <thread>
 
@@ -53,29 +54,41 @@ namespace {
     fprintf(f, "ply\nformat ascii 1.0\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\n", nv);
     fprintf(f, "property uchar red\nproperty uchar green\nproperty uchar blue\nelement face %zu\n", nf);
     fprintf(f, "property list uchar int vertex_indices\nend_header\n");
+    // Batches of nthr x 64 Ki lines are formatted by nthr threads into reusable raw buffers (no zero
+    // fill) while the previous batch is being written: formatting and fwrite overlap.
     const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t chunk  = 1 << 16;
     auto emit = [&](size_t total, size_t max_line, auto&& line) {
-      const size_t chunk = 1 << 16;
-      for (size_t base = 0; base < total; base += chunk * nthr) {
-        std::vector<std::string> out(nthr);
+      std::unique_ptr<char[]> buf[2];
+      std::vector<size_t> len[2];
+      for (int k = 0; k < 2; ++k) {
+        buf[k].reset(new char[(size_t) nthr * chunk * max_line]);
+        len[k].assign(nthr, 0);
+      }
+      std::thread writer;
+      int cur = 0;
+      for (size_t base = 0; base < total; base += chunk * nthr, cur ^= 1) {
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nthr; ++t)
-          th.emplace_back([&, t] {
-            const size_t lo = base + t * chunk, hi = std::min(total, lo + chunk);
-            if (lo >= hi)
-              return;
-            std::string& s = out[t];
-            s.resize((hi - lo) * max_line);
+          th.emplace_back([&, t, cur, base] {
+            const size_t lo = std::min(total, base + t * chunk), hi = std::min(total, lo + chunk);
+            char* dst  = buf[cur].get() + (size_t) t * chunk * max_line;
             size_t pos = 0;
             for (size_t i = lo; i < hi; ++i)
-              pos += line(i, &s[pos]);
-            s.resize(pos);
+              pos += line(i, dst + pos);
+            len[cur][t] = pos;
           });
         for (auto& x : th)
           x.join();
-        for (auto& s : out)
-          fwrite(s.data(), 1, s.size(), f);
+        if (writer.joinable())
+          writer.join(); // the other buffer set is free again, and the file stays in order
+        writer = std::thread([&, cur] {
+          for (unsigned t = 0; t < nthr; ++t)
+            fwrite(buf[cur].get() + (size_t) t * chunk * max_line, 1, len[cur][t], f);
+        });
       }
+      if (writer.joinable())
+        writer.join();
     };
     const double* V = mesh.vertices.data();
     const double* C = mesh.colors.data();
@@ -258,6 +271,17 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
   if (path)
     write_mesh_ply(path, m->mesh);
   m->mesh_ms_ply = now_ms() - t_ply;
+  return 0;
+}
+
+int mrh_write_mesh_ply(const char* path, const double* vertices, const double* colors, const int32_t* faces, size_t n_vertices, size_t n_faces) {
+  if (!path || (n_vertices && (!vertices || !colors)) || (n_faces && !faces))
+    return fail("null argument");
+  HostMesh mesh;
+  mesh.vertices.assign(vertices, vertices + 3 * n_vertices);
+  mesh.colors.assign(colors, colors + 3 * n_vertices);
+  mesh.faces.assign(faces, faces + 3 * n_faces);
+  write_mesh_ply(path, mesh);
   return 0;
 }
 

@@ -132,3 +132,34 @@ def test_ply_number_formatter_equals_printf_g():
                 assert buf.raw[:k].decode() == "%g" % x, x
                 n += 1
     assert n > 300000
+
+
+def test_ascii_ply_writer_on_the_host(tmp_path):
+    """The mesh PLY writer of extractMesh (geowrapper.cpp:194-229: ASCII, `ostream << double`, colours cast
+    to uchar) through its handle-free hook: header, every line byte for byte against printf, across the
+    batch boundaries of the pipelined writer (batch = threads x 65536 lines)."""
+    import ctypes as C
+
+    from mrhash_b200 import _capi
+
+    lib = _capi.lib()
+    rng = np.random.default_rng(12)
+    nv, nf = 1_200_000, 300_001
+    V = (rng.random((nv, 3)) * 8 - 4).astype(np.float32).astype(np.float64)
+    V[:5] = [[0, -0.0, 1], [1e-5, 123456.5, -2.5], [0.1, 0.25, 1e6], [-3.0000001, 2.9999998, 0.015625], [1e-4, 9.99999e-5, 999999.5]]
+    Cc = rng.random((nv, 3)) * 300 - 20  # un-normalised colours wrap like the reference's uchar cast (Q4)
+    F = rng.integers(0, nv, size=(nf, 3)).astype(np.int32)
+    path = str(tmp_path / "mesh.ply")
+    assert lib.mrh_write_mesh_ply(path.encode(), V.ctypes.data, Cc.ctypes.data, F.ctypes.data, nv, nf) == 0
+    lines = open(path).read().split("\n")
+    h = lines.index("end_header")
+    assert lines[:h] == ["ply", "format ascii 1.0", f"element vertex {nv}", "property float x", "property float y", "property float z", "property uchar red",
+                         "property uchar green", "property uchar blue", f"element face {nf}", "property list uchar int vertex_indices"]
+    assert len(lines) == h + 1 + nv + nf + 1 and lines[-1] == ""
+    idx = np.unique(np.concatenate([np.arange(0, 2000), np.arange(65536 - 50, 65536 + 50), np.arange(8 * 65536 - 50, 8 * 65536 + 50), np.arange(16 * 65536 - 50, 16 * 65536 + 50),
+                                    rng.integers(0, nv, 20000), np.arange(nv - 2000, nv)]))
+    for i in idx.tolist():
+        v, c = V[i], Cc[i]
+        assert lines[h + 1 + i] == "%g %g %g %d %d %d" % (v[0], v[1], v[2], int(c[0]) & 0xFF, int(c[1]) & 0xFF, int(c[2]) & 0xFF), i
+    for i in np.unique(np.concatenate([np.arange(0, 2000), rng.integers(0, nf, 20000), np.arange(nf - 2000, nf)])).tolist():
+        assert lines[h + 1 + nv + i] == "3 %d %d %d" % tuple(F[i]), i
