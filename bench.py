@@ -369,8 +369,10 @@ def main():
     depth_np, rgb_np = depth_h.numpy(), rgb_h.numpy()
     g = new_map(args, rank, world, local, max_num_triangles=4_000_000 if world > 1 else 1)
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
-    bcast_d = torch.empty((args.height, args.width), dtype=torch.float32, device=dev) if world > 1 else None
-    bcast_c = torch.empty((args.height, args.width, 3), dtype=torch.uint8, device=dev) if world > 1 else None
+    # N > 1: depth and colour travel in ONE buffer, one NCCL broadcast per frame
+    bcast = torch.empty(7 * P, dtype=torch.uint8, device=dev) if world > 1 else None
+    bcast_d = bcast[: 4 * P].view(torch.float32).view(args.height, args.width) if world > 1 else None
+    bcast_c = bcast[4 * P :].view(args.height, args.width, 3) if world > 1 else None
     ev_ready, ev_done = torch.cuda.Event(), torch.cuda.Event()
     ev_done.record(stream)
 
@@ -400,8 +402,7 @@ def main():
         if rank == 0:
             bcast_d.copy_(depth_h[k], non_blocking=True)
             bcast_c.copy_(rgb_h[k], non_blocking=True)
-        dist.broadcast(bcast_d, 0)
-        dist.broadcast(bcast_c, 0)
+        dist.broadcast(bcast, 0)
         ev_ready.record()
         stream.wait_event(ev_ready)
         g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
