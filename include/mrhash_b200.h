@@ -222,6 +222,16 @@ int mrh_get_stream(mrh_map* m, void** stream);
 /* number of kernel launches issued by this handle so far */
 int mrh_get_launch_count(mrh_map* m, uint64_t* n);
 
+/* Test hook for the shared-reciprocal divisions of the frame kernel (csrc/mrh_div.cuh, which replace the
+ * `a / b` of voxel_hash_utils.cuh:75-151,169-181, camera.cuh:131-160 and voxel_data_structures.cu:803-822):
+ * compares them with IEEE division on the device for every one of the 2^32 numerator bit patterns of
+ * `divisor` (skipped when divisor <= 0) and for n_random (numerator, divisor) pairs; *mismatches = number
+ * of quotients whose bits differ. */
+int mrh_selftest_div(int device, float divisor, uint64_t n_random, uint64_t seed, uint64_t* mismatches);
+/* radius (in voxels) inside which the integer voxel -> block shortcut of the ray walk was verified to
+ * equal the reference's metric arithmetic for the handle's current voxel size (0: shortcut unused) */
+int mrh_get_block_shortcut_radius(mrh_map* m, int* radius);
+
 /* Parity dump: live block records sorted by (x, y, z) and their voxels as 12-byte reference Voxel
  * structs {f32 sdf, f32 sum_squared, u8 r, g, b, weight} (512 per record; resolution-1 records use
  * the first 64). Returns the number of live blocks in *n_out; fills at most max_entries. */

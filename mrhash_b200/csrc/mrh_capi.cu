@@ -87,6 +87,11 @@ static int alloc_map(mrh_map* m) {
   CK(cudaMalloc(&d.live[0], sizeof(LiveEntry) * N * 2));
   CK(cudaMalloc(&d.live[1], sizeof(LiveEntry) * N * 2));
   CK(cudaMalloc(&d.vis, sizeof(VisEntry) * N * 2));
+  CK(cudaMalloc(&d.fq, sizeof(FuseEntry) * N * 2));
+  CK(cudaMemset(d.fq, 0, sizeof(FuseEntry) * N * 2)); // tag 0 is never used by a frame
+  CK(cudaMalloc(&d.gc_list, sizeof(GcEntry) * N * 2));
+  CK(cudaMalloc(&d.fqs, sizeof(FrameQueues)));
+  CK(cudaMemset(d.fqs, 0, sizeof(FrameQueues)));
   CK(cudaMalloc(&d.realloc_list, sizeof(VisEntry) * N));
   CK(cudaMalloc(&d.reint_keys, sizeof(unsigned long long) * N));
   CK(cudaMalloc(&d.ctr, sizeof(Counters)));
@@ -101,6 +106,7 @@ int mrh::reset_map(mrh_map* m) {
   CK(cudaMemsetAsync(d.carved, 0, d.num_blocks, m->stream));
   k_init_heap<<<592, 256, 0, m->stream>>>(d.heap, d.stats, d.num_blocks);
   k_init_counters<<<1, 1, 0, m->stream>>>(d.ctr, d.num_blocks);
+  CK(cudaMemsetAsync(d.fqs, 0, sizeof(FrameQueues), m->stream));
   m->launches += 2;
   m->live_cur       = 0;
   m->counters_clean = true;
@@ -111,7 +117,7 @@ int mrh::reset_map(mrh_map* m) {
 static void free_map(mrh_map* m) {
   MapDev& d = m->dev;
   cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.carved), cudaFree(d.stats);
-  cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.realloc_list), cudaFree(d.reint_keys), cudaFree(d.ctr), cudaFree(d.zbuf);
+  cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.fq), cudaFree(d.gc_list), cudaFree(d.fqs), cudaFree(d.realloc_list), cudaFree(d.reint_keys), cudaFree(d.ctr), cudaFree(d.zbuf);
   for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
     for (int i = 0; i < 2; ++i) {
       cudaFree(in->d_buf[i]), cudaFreeHost(in->h_buf[i]);
@@ -158,6 +164,14 @@ static void refresh_map_params(mrh_map* m) {
   d.min_weight_threshold = p.min_weight_threshold;
   d.projective           = p.projective_sdf;
   d.mc_threshold         = p.marching_cubes_threshold;
+  // shared-reciprocal divisions (mrh_div.cuh): every shared divisor must lie in the exponent window
+  const float lo = 9.094947017729282e-13f, hi = 1.099511627776e12f; // 2^-40, 2^40
+  const float vs = p.virtual_voxel_size;
+  d.fast_div     = vs * 0.5f >= lo && vs * 8.f <= hi && m->cam.min_depth >= lo && m->cam.max_depth <= hi && p.integration_weight_sample >= 1 && p.integration_weight_sample <= (1 << 20) &&
+                   !getenv("MRH_NO_FAST_DIV");
+  d.block_shortcut_radius = 0;
+  if (d.fast_div && m->shortcut_size == vs && m->shortcut_ext == d.ext[0])
+    d.block_shortcut_radius = m->shortcut_radius;
   if (p.shard_world > 1) {
     d.shard_lo = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) p.shard_rank / (uint64_t) p.shard_world);
     d.shard_hi = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) (p.shard_rank + 1) / (uint64_t) p.shard_world);
@@ -310,6 +324,15 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("MRH_PDL"))
     m->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("MRH_FRAME"))
+    m->use_fused = strcmp(e, "split") != 0;
+  if (const char* e = getenv("MRH_BULK_DEPTH"))
+    m->use_bulk_depth = atoi(e) != 0;
+  if (const char* e = getenv("MRH_FUSED_PREF")) { // "num/den": CTAs that look at the fusion queue first
+    int a = 1, b = 4;
+    if (sscanf(e, "%d/%d", &a, &b) == 2 && b > 0 && a >= 0)
+      m->fused_pref_num = a, m->fused_pref_den = b;
+  }
   {
     const char* e      = getenv("MRH_INTEGRATE_CTAS_PER_SM");
     const int per_sm   = e ? std::max(1, atoi(e)) : integrate_ctas_per_sm(); // one wave of resident CTAs
@@ -494,8 +517,48 @@ int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* norma
   return 0;
 }
 
+// voxel_to_block_1 (voxel_hash_utils.cuh:75-103) is a function of the integer voxel coordinate alone;
+// for voxel_extents_scale = 1 it should be v >> 3, but it is computed in metres with a 1e-5 slack, so
+// float rounding can disagree far from the origin. One kernel evaluates it for every coordinate of
+// the key range and reports the smallest |v| where the two differ: inside that radius the ray walk
+// takes the integer shortcut, outside it the reference arithmetic.
+namespace {
+  __global__ void k_verify_block_shortcut(float size, float ext, int* min_bad) {
+    const int n = 1 << 24;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const int v = i - (1 << 23);
+      if (voxel_to_block_1(v, size, ext) != (v >> 3))
+        atomicMin(min_bad, v < 0 ? -v : v);
+    }
+  }
+} // namespace
+
+static int verify_block_shortcut(mrh_map* m, float size, float ext, int* radius) {
+  *radius = 0;
+  if (ext != 1.f)
+    return 0;
+  int* d_min = nullptr;
+  CK(cudaMalloc(&d_min, sizeof(int)));
+  const int init = 1 << 23;
+  CK(cudaMemcpyAsync(d_min, &init, sizeof(int), cudaMemcpyHostToDevice, m->stream));
+  k_verify_block_shortcut<<<m->num_sms * 8, 256, 0, m->stream>>>(size, ext, d_min);
+  m->launches += 1;
+  int h_min = 0;
+  CK(cudaMemcpyAsync(&h_min, d_min, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaStreamSynchronize(m->stream));
+  cudaFree(d_min);
+  *radius = std::max(0, h_min - 1);
+  return 0;
+}
+
 static int compute_frame(mrh_map* m) {
   const bool rgbd = m->depth_ptr && m->rgb_ptr;
+  if (rgbd && m->use_fused && (m->shortcut_size != m->p.virtual_voxel_size || m->shortcut_ext != (float) m->p.voxel_extents_scale)) {
+    // first frame with these parameters: verify the integer voxel -> block shortcut once
+    m->shortcut_size = m->p.virtual_voxel_size, m->shortcut_ext = (float) m->p.voxel_extents_scale;
+    if (verify_block_shortcut(m, m->shortcut_size, m->shortcut_ext, &m->shortcut_radius))
+      return 1;
+  }
   if (rgbd) {
     if (m->depth_rows != (int) m->cam.rows || m->depth_cols != (int) m->cam.cols || m->rgb_rows != m->depth_rows || m->rgb_cols != m->depth_cols)
       return fail("mrh_compute: depth %dx%d / rgb %dx%d do not match the camera %ux%u", m->depth_rows, m->depth_cols, m->rgb_rows, m->rgb_cols, m->cam.rows, m->cam.cols);
@@ -537,6 +600,25 @@ static int compute_frame(mrh_map* m) {
       CK(cudaEventSynchronize(in->copied[in->which]));
       in->pending_direct = false;
     }
+  return 0;
+}
+
+/* tuning builds (-DMRH_FUSED_DEBUG): reads the 32 timer words of the fused kernel and re-arms them */
+extern "C" int mrh_debug_timers(mrh_map* m, unsigned long long out[32]) {
+  GUARD(m);
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(out, (char*) m->dev.ctr + offsetof(Counters, dbg), 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long init[32];
+  memset(init, 0, sizeof(init));
+  init[0] = init[2] = ~0ull;
+  CK(cudaMemcpy((char*) m->dev.ctr + offsetof(Counters, dbg), init, sizeof(init), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int mrh_get_block_shortcut_radius(mrh_map* m, int* radius) {
+  if (!m || !radius)
+    return fail("null argument");
+  *radius = m->dev.block_shortcut_radius;
   return 0;
 }
 
@@ -672,6 +754,8 @@ int mrh_get_stats(mrh_map* m, mrh_stats* out) {
   CK(cudaMemcpyAsync(m->h_ctr, m->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
   const Counters& c   = *m->h_ctr;
+  if (c.fault)
+    return fail("frame kernel watchdog: a wait inside k_frame hit its iteration bound (internal error, results are invalid)");
   out->frames         = m->frames_total;
   out->rays_valid     = c.rays_valid;
   out->blocks_new     = c.blocks_new;

@@ -12,6 +12,7 @@
 
 #include "mrh_host.h"
 #include "mrh_fast.cuh"
+#include "mrh_fused.cuh"
 #include "mrh_kernels.cuh"
 #include "mrh_points.cuh"
 #include "mrh_var.cuh"
@@ -201,6 +202,35 @@ int carve_low_blocks(mrh_map* m, uint32_t n_low) {
   return 0;
 }
 
+namespace {
+  // the fused frame kernel (mrh_fused.cuh): one persistent launch per frame
+  using FrameKernel = void (*)(MapDev, FrameDev, CameraDev, const float*, const uint8_t*, uint32_t, int, int, uint32_t, uint32_t, uint32_t);
+  FrameKernel frame_kernel(bool gc, int model, bool fast) {
+    if (model == 0 && fast)
+      return gc ? k_frame<true, 0, true> : k_frame<false, 0, true>;
+    if (model == 0)
+      return gc ? k_frame<true, 0, false> : k_frame<false, 0, false>;
+    return gc ? k_frame<true, 1, false> : k_frame<false, 1, false>;
+  }
+} // namespace
+
+// resident CTAs of the fused kernel on the whole device (every instance is compiled for the same bound)
+int fused_grid(mrh_map* m) {
+  if (m->fused_grid > 0)
+    return m->fused_grid;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_kernel(true, 0, true), kFuThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int other = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&other, frame_kernel(true, 1, false), kFuThreads, 0) == cudaSuccess && other >= 1)
+    per_sm = std::min(per_sm, other);
+  if (const char* e = getenv("MRH_FUSED_CTAS_PER_SM"))
+    per_sm = std::max(1, std::min(per_sm, atoi(e)));
+  m->fused_ctas_per_sm = per_sm;
+  m->fused_grid        = m->num_sms * per_sm;
+  return m->fused_grid;
+}
+
 int integrate_rgbd(mrh_map* m) {
   FrameCtx c         = begin_frame(m);
   const MapDev& d    = m->dev;
@@ -213,7 +243,32 @@ int integrate_rgbd(mrh_map* m) {
       cudaEventRecord(m->ev_k[i], s);
   };
   const bool fused_gc = c.gc && !c.starve && !c.var;
-  if (!c.var) {
+  if (!c.var && m->use_fused) {
+    // one persistent launch (mrh_fused.cuh)
+    if (!m->counters_clean) {
+      k_zero_frame_counters<<<1, 1, 0, s>>>(d, f.live_cur ^ 1u);
+      m->launches += 1;
+    }
+    const uint32_t tiles_x = (k.cols + kTileW - 1) / kTileW, tiles_y = (k.rows + kTileH - 1) / kTileH;
+    const int rearm        = c.starve ? 0 : 1;
+    FrameDev ff            = f;
+    ff.tag                 = ++m->fuse_tag;
+    ff.band_lo             = 0;
+    ff.band_hi             = tiles_x * tiles_y;
+    // cp.async.bulk needs 16-byte aligned rows: image width a multiple of 4 pixels, aligned base
+    const int bulk_depth = m->use_bulk_depth && (k.cols % 4u) == 0 && ((uintptr_t) m->depth_ptr % 16u) == 0 ? 1 : 0;
+    if (m->rgb_ready)
+      cudaStreamWaitEvent(s, m->rgb_ready, 0);
+    mark(0);
+    launch_chained(frame_kernel(fused_gc, k.model, d.fast_div != 0 && k.model == 0), dim3(fused_grid(m)), dim3(kFuThreads), s, m->use_pdl && m->counters_clean, d, ff, k, m->depth_ptr, m->rgb_ptr, tiles_x, rearm, bulk_depth,
+                   (uint32_t) m->num_sms, (uint32_t) m->fused_pref_num, (uint32_t) m->fused_pref_den);
+    CKL();
+    mark(1);
+    mark(2);
+    mark(3);
+    m->launches += 1;
+    m->counters_clean = rearm != 0;
+  } else if (!c.var) {
     // two-launch frame (mrh_fast.cuh)
     if (!m->counters_clean) {
       k_zero_frame_counters<<<1, 1, 0, s>>>(d, f.live_cur ^ 1u);
@@ -287,6 +342,7 @@ int integrate_rgbd(mrh_map* m) {
   end_frame(c, swapped_twice, !c.var && !c.starve);
   return 0;
 }
+
 
 // integrate3D (:1381-1401): emit -> stable sort by voxel address -> apply. K is the key type.
 template <typename K>
@@ -385,3 +441,73 @@ int integrate_points(mrh_map* m) {
 }
 
 } // namespace mrh
+
+// ---------------------------------------------------------------------------------------------
+// self-test of mrh_div.cuh (declared in include/mrhash_b200.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+  __device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    x ^= x >> 33, x *= 0xff51afd7ed558ccdull, x ^= x >> 33, x *= 0xc4ceb9fe1a85ec53ull, x ^= x >> 33;
+    return (uint32_t) x;
+  }
+  __global__ void k_selftest_div_all(float b, unsigned long long* bad) {
+    const float y1 = mrh::div_recip(b);
+    unsigned long long n = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; i < (1ull << 32); i += (unsigned long long) gridDim.x * blockDim.x) {
+      const float a = __uint_as_float((uint32_t) i);
+      const float q = mrh::div_fast(a, b, y1), r = __fdiv_rn(a, b);
+      if (__float_as_uint(q) != __float_as_uint(r) && !(q != q && r != r))
+        ++n;
+      const float qs = mrh::div_fast_signed(a, -b, y1), rs = __fdiv_rn(a, -b);
+      if (__float_as_uint(qs) != __float_as_uint(rs) && !(qs != qs && rs != rs))
+        ++n;
+    }
+    if (n)
+      atomicAdd(bad, n);
+  }
+  __global__ void k_selftest_div_random(unsigned long long n_pairs, unsigned long long seed, unsigned long long* bad) {
+    unsigned long long n = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long) blockDim.x + threadIdx.x; i < n_pairs; i += (unsigned long long) gridDim.x * blockDim.x) {
+      const float a = __uint_as_float(mix32(seed + 2 * i));
+      // divisor: any sign-less float inside the window the kernels guarantee (2^-40 .. 2^40)
+      const uint32_t e = 87u + mix32(seed + 2 * i + 1) % 81u;
+      const float b    = __uint_as_float((e << 23) | (mix32(seed ^ (i * 0x9E3779B97F4A7C15ull)) & 0x7FFFFFu));
+      if (!mrh::div_range_ok(b))
+        continue;
+      const float q = mrh::div_fast(a, b, mrh::div_recip(b)), r = __fdiv_rn(a, b);
+      if (__float_as_uint(q) != __float_as_uint(r) && !(q != q && r != r))
+        ++n;
+    }
+    if (n)
+      atomicAdd(bad, n);
+  }
+} // namespace
+
+extern "C" int mrh_selftest_div(int device, float divisor, uint64_t n_random, uint64_t seed, uint64_t* mismatches) {
+  using mrh::fail;
+  if (!mismatches)
+    return fail("null argument");
+  if (cudaSetDevice(device < 0 ? 0 : device) != cudaSuccess)
+    return fail("no CUDA device: libmrhash_b200 has no CPU path");
+  unsigned long long* d_bad = nullptr;
+  if (cudaMalloc(&d_bad, sizeof(unsigned long long)) != cudaSuccess || cudaMemset(d_bad, 0, sizeof(unsigned long long)) != cudaSuccess)
+    return fail("selftest: allocation failed");
+  if (divisor > 0.f) {
+    const float ad = divisor;
+    if (!(ad >= 9.094947017729282e-13f && ad <= 1.099511627776e12f)) {
+      cudaFree(d_bad);
+      return fail("selftest: divisor outside the window of the shared-reciprocal division");
+    }
+    k_selftest_div_all<<<148 * 16, 256>>>(divisor, d_bad);
+  }
+  if (n_random)
+    k_selftest_div_random<<<148 * 16, 256>>>(n_random, seed, d_bad);
+  unsigned long long h = 0;
+  const cudaError_t e = cudaMemcpy(&h, d_bad, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess)
+    return fail("selftest: %s", cudaGetErrorString(e));
+  *mismatches = h;
+  return 0;
+}
+

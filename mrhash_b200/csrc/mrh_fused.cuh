@@ -1,0 +1,938 @@
+// mrh_fused.cuh — the RGB-D frame as ONE persistent kernel (single resolution: sdf_var_threshold = 0,
+// the configuration every shipped RGB-D config uses).
+//
+// Replaces, for VoxelContainer::integrate (voxel_data_structures.cpp:90-134; files under
+// /root/reference/mrhash/src/sdf): calculateCloudKernel (camera.cu:5-26), allocBlocksKernel + its host
+// retry loop (voxel_data_structures.cu:758-922), resetCompactHashTable + flatAndReduceHashTable
+// (:9-14, :406-449), integrateDepthMapKernel (:1095-1181) and, fused, garbageCollectIdentify / Free
+// (:1674-1724, :1827-1854).
+//
+// k_frame is launched with exactly as many CTAs as are resident at once (SMs x occupancy). Every
+// CTA loops over work items taken from three queues in global memory:
+//   chunk  128 entries of the input live list: frustum test (isSDFBlockInCameraFrustumApprox),
+//          live-list compaction, visible list; blocks that can receive depth this frame are
+//          appended to the fusion queue fq[];
+//   tile   32 x 4 depth pixels: the depth rows arrive in shared memory through cp.async.bulk on an
+//          mbarrier; each warp walks the block DDA of an 8 x 4 pixel patch; visited keys are
+//          de-duplicated in a per-CTA shared-memory set and each distinct key is resolved once by a
+//          warp-cooperative find-or-insert on the 128-byte bucket rows; a new block goes straight to
+//          the output live list, the visible list and fq[];
+//   fuse   one entry of fq[]: the block's three planes (6 KB, contiguous) are pulled into shared
+//          memory by ONE cp.async.bulk issued before the projection pass and awaited on an mbarrier
+//          after it; 4 consecutive-x voxels per thread, 128-bit shared loads and global stores.
+// Blocks that already existed do not depend on the ray walk, so fusion of the visible list overlaps
+// it; blocks inserted by the walk are fused as they appear. Removing a block (GC) is deferred to the
+// finaliser (the last CTA to finish): during the frame no key ever leaves the table, so a walker can
+// never re-insert a block that the reference would still have seen (its GC runs after allocation),
+// and the free stack receives the freed blocks after every allocation of the frame, as in the reference.
+// No CTA ever waits for a specific other CTA: items are claimed dynamically, and a CTA that finds
+// nothing to do polls the producer-completion counters.
+#pragma once
+#include "mrh_div.cuh"
+#include "mrh_kernels.cuh"
+
+namespace mrh {
+
+constexpr int kFuThreads = 128;
+constexpr int kFuWarps   = kFuThreads / 32;
+constexpr int kTileW     = 32; // one 128-byte depth row segment per bulk copy
+constexpr int kTileH     = 4;
+constexpr int kSetCells  = 128; // per-tile set of resolved block keys
+constexpr unsigned long long kStatsOnly = 1ull << 63;
+
+#ifndef MRH_FUSED_MIN_CTAS
+#define MRH_FUSED_MIN_CTAS 8
+#endif
+
+enum : int { kItemExit = 0, kItemChunk = 1, kItemTile = 2, kItemFuse = 3 };
+
+#ifdef MRH_FUSED_DEBUG
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_ADD(i, v) atomicAdd(&m.ctr->dbg[i], (unsigned long long) (v))
+#define DBG_MAX(i, v) atomicMax(&m.ctr->dbg[i], (unsigned long long) (v))
+#define DBG_MIN(i, v) atomicMin(&m.ctr->dbg[i], (unsigned long long) (v))
+#endif
+
+// ---- async-proxy helpers (PTX: mbarrier + cp.async.bulk; SASS: SYNCS / UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+// Every wait in this file is bounded (a bound is only ever reached through a bug): it sets the sticky
+// fault word, which fails the next mrh_get_stats / mrh_synchronize, instead of hanging the device.
+constexpr uint32_t kSpinBound = 1u << 22;
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity, uint32_t* fault) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > kSpinBound) {
+      *reinterpret_cast<volatile uint32_t*>(fault) = 1u;
+      return;
+    }
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) {
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+}
+__device__ __forceinline__ uint4 ld_vol_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct FusedItem {
+  int kind;
+  uint32_t arg;
+  uint32_t pad[2];
+  FuseEntry e;
+};
+
+struct FusedSmem {
+  alignas(128) uint32_t planes[kBlockBytes / 4]; // sdf[512] | sum_squared[512] | rgbw[512] of the block being fused
+  alignas(128) float depth[2][kTileH][kTileW];   // depth rows of the current / next tile
+  unsigned long long set[2][kSetCells];          // resolved keys of the current tile; the other one is being cleared
+  unsigned long long bar_planes;
+  unsigned long long bar_depth[2];
+  FusedItem item[2];
+  float red_min[kFuWarps];
+  uint32_t red_max[kFuWarps];
+  uint32_t red_upd[kFuWarps];
+  uint32_t warps_done; // warps of this CTA that have finished a chunk / tile item (every 4th completes an item)
+  uint32_t rays;       // valid rays walked by this CTA
+  int last;
+};
+
+// one warp of the CTA has finished its share of a chunk / tile item; the last of the four reports the item
+__device__ __forceinline__ void item_warp_done(const MapDev& m, FusedSmem& sm) {
+  const uint32_t n = atomicAdd(&sm.warps_done, 1u) + 1u;
+  if ((n & (kFuWarps - 1)) == 0)
+    atomicAdd(&m.fqs->items_done.v, 1u);
+}
+
+// division by a shared divisor: FAST = the compiler's own sequence with the reciprocal hoisted (mrh_div.cuh)
+template <bool FAST>
+__device__ __forceinline__ float recip_of(float b) {
+  return FAST ? div_recip(b) : 0.f;
+}
+template <bool FAST>
+__device__ __forceinline__ float qdiv(float a, float b, float y1) {
+  return FAST ? div_fast(a, b, y1) : fdiv(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fusion queue
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fq_write(const MapDev& m, uint32_t qi, uint32_t tag, unsigned long long key, uint32_t val, uint32_t slot, uint32_t live_idx, uint32_t vis_idx) {
+  FuseEntry* e = m.fq + qi;
+  st_v4(reinterpret_cast<char*>(e) + 16, slot, live_idx, vis_idx, tag);
+  st_v4(e, (uint32_t) key, (uint32_t) (key >> 32), val, tag);
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk role: visibility pass over 128 entries of the input live list
+// ---------------------------------------------------------------------------------------------
+template <bool FUSE_GC>
+__device__ __forceinline__ void role_chunk(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, uint32_t chunk, uint32_t n_live, FusedSmem& sm) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int lane      = threadIdx.x & 31;
+  const uint32_t cur  = f.live_cur;
+  const uint32_t i    = chunk * kFuThreads + threadIdx.x;
+  LiveEntry le        = {kEmpty, kInvalid, 0u};
+  if (i < n_live)
+    le = m.live[cur][i];
+  const uint32_t slot = le.slot;
+  const bool alive    = slot != kInvalid;
+  i3 b                = {0, 0, 0};
+  bool vis = false, maybe = true;
+  if (alive) {
+    b   = unpack_key(le.key);
+    vis = block_in_frustum_ex(cam, pose, b, m.voxel_size, maybe);
+  }
+  // a visible block whose voxels cannot land in the image only matters if its stored statistics say
+  // it must be collected (never in a steady stream: it would have been collected when last updated)
+  bool enqueue = vis && !(le.val & 0x80000000u);
+  if (enqueue && !maybe) {
+    enqueue = false;
+    if (FUSE_GC) {
+      const BlockStats st = m.stats[le.val];
+      enqueue             = gc_predicate(m, st.min_abs_sdf, st.max_weight);
+    }
+  }
+  const unsigned am = __ballot_sync(full, alive);
+  const unsigned vm = __ballot_sync(full, vis);
+  const unsigned qm = __ballot_sync(full, enqueue);
+  uint32_t abase = 0, vbase = 0, qbase = 0;
+  if (lane == 0) {
+    if (am)
+      abase = atomicAdd(&m.ctr->live_count[cur ^ 1u], (uint32_t) __popc(am));
+    if (vm)
+      vbase = atomicAdd(&m.ctr->vis_count, (uint32_t) __popc(vm));
+    if (qm)
+      qbase = atomicAdd(&m.fqs->fq_count.v, (uint32_t) __popc(qm));
+  }
+  abase                = __shfl_sync(full, abase, 0);
+  vbase                = __shfl_sync(full, vbase, 0);
+  qbase                = __shfl_sync(full, qbase, 0);
+  const unsigned lt    = (1u << lane) - 1u;
+  const uint32_t my_li = abase + __popc(am & lt);
+  const uint32_t my_vi = vbase + __popc(vm & lt);
+  if (alive)
+    m.live[cur ^ 1u][my_li] = le;
+  if (vis) {
+    VisEntry e;
+    e.x = b.x, e.y = b.y, e.z = b.z;
+    e.val            = le.val;
+    e.slot           = slot;
+    e.live_idx       = my_li;
+    e.maybe_in_image = maybe ? 1u : 0u;
+    e.pad1           = 0;
+    m.vis[my_vi]     = e;
+  }
+  if (enqueue)
+    fq_write(m, qbase + __popc(qm & lt), f.tag, le.key | (maybe ? 0ull : kStatsOnly), le.val, slot, my_li, my_vi);
+  // the counters above were bumped by atomics whose results this warp has received: whoever sees the
+  // completion count sees them too (both are resolved in L2)
+  if (lane == 0)
+    item_warp_done(m, sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile role: ray walk + block allocation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool key_in_range_margin(i3 b, int margin) {
+  const unsigned span = 2u * (unsigned) (kCoordBias - margin);
+  return (unsigned) (b.x + kCoordBias - margin) < span && (unsigned) (b.y + kCoordBias - margin) < span && (unsigned) (b.z + kCoordBias - margin) < span;
+}
+__device__ __forceinline__ uint32_t set_hash(unsigned long long k) {
+  const uint32_t x = (uint32_t) k ^ ((uint32_t) (k >> 21) * 0x9E3779B1u) ^ ((uint32_t) (k >> 42) * 0x85EBCA6Bu);
+  return (x ^ (x >> 15)) & (kSetCells - 1);
+}
+// true when the key has been resolved for this tile already
+__device__ __forceinline__ bool set_contains(const unsigned long long* set, unsigned long long key) {
+  uint32_t h = set_hash(key);
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const unsigned long long c = *reinterpret_cast<const volatile unsigned long long*>(set + h);
+    if (c == key)
+      return true;
+    if (c == kNoKey)
+      return false;
+    h = (h + 1) & (kSetCells - 1);
+  }
+  return false;
+}
+__device__ __forceinline__ void set_insert(unsigned long long* set, unsigned long long key) {
+  uint32_t h = set_hash(key);
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const unsigned long long old = atomicCAS(set + h, kNoKey, key);
+    if (old == kNoKey || old == key)
+      return;
+    h = (h + 1) & (kSetCells - 1);
+  }
+  // no room within the probe limit: the key simply stays unresolved for this tile (it is looked up again)
+}
+
+// Warp-cooperative find-or-insert of one block (allocBlock, voxel_data_structures.cu:502-624, without
+// the bucket mutex): same protocol as warp_insert (mrh_table.cuh), new blocks are published to the
+// output live list, the visible list and the fusion queue.
+__device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& cam, const PoseDev& pose, const FrameDev& f, unsigned long long key, int lane) {
+  const unsigned full = 0xFFFFFFFFu;
+  const i3 b          = unpack_key(key);
+  const uint32_t h    = block_hash_fast(m, b);
+  if (h < m.shard_lo || h >= m.shard_hi)
+    return; // another GPU owns this bucket range
+  bool frustum_ok = false;
+#pragma unroll 1
+  for (int attempt = 0; attempt < 1024; ++attempt) {
+    int free_slot                    = -1;
+    unsigned long long free_expected = kEmpty;
+    bool found = false, end = false;
+#pragma unroll 1
+    for (int w = 0; w < kMaxWindows && !end; ++w) {
+      uint32_t bkt = h + 2u * w + (lane >> 4);
+      if (bkt >= m.num_buckets)
+        bkt %= m.num_buckets;
+      const uint32_t slot        = bkt * kBucketSlots + (lane & 15);
+      const unsigned long long k = attempt == 0 ? m.keys[slot] : ld_cg_u64(m.keys + slot);
+      if (__ballot_sync(full, k == key)) {
+        found = true;
+        break;
+      }
+      const unsigned fr = __ballot_sync(full, k == kEmpty || k == kTomb);
+      const unsigned em = __ballot_sync(full, k == kEmpty);
+      if (free_slot < 0 && fr) {
+        const int src = __ffs(fr) - 1;
+        free_slot     = (int) __shfl_sync(full, slot, src);
+        free_expected = __shfl_sync(full, k, src);
+      }
+      end = em != 0;
+    }
+    if (found)
+      return;
+    if (free_slot < 0) {
+      if (lane == 0)
+        atomicAdd(&m.ctr->dropped_table, 1ull);
+      return;
+    }
+    if (!frustum_ok) {
+      const bool in = lane < 8 && block_corner_in_frustum(cam, pose, b, lane, m.voxel_size);
+      if (!__ballot_sync(full, in))
+        return;
+      frustum_ok = true;
+    }
+    unsigned long long prev = 0;
+    if (lane == 0)
+      prev = atomicCAS(m.keys + free_slot, free_expected, key);
+    prev = __shfl_sync(full, prev, 0);
+    if (prev == free_expected) {
+      if (lane == 0) {
+        const int addr = atomicSub(&m.ctr->heap_counter, 1); // consumeHeapHigh (:33-40)
+        if (addr < 0) {
+          atomicAdd(&m.ctr->heap_counter, 1);
+          atomicExch(m.keys + free_slot, kTomb);
+          atomicAdd(&m.ctr->dropped_heap, 1ull);
+        } else {
+          const uint32_t val = m.heap[addr];
+          m.stats[val]       = {3.40282346638528859812e+38f, 0u};
+          m.vals[free_slot]  = val;
+          const uint32_t out = f.live_cur ^ 1u;
+          const uint32_t li  = atomicAdd(&m.ctr->live_count[out], 1u);
+          m.live[out][li]    = {key, (uint32_t) free_slot, val};
+          const uint32_t vi  = atomicAdd(&m.ctr->vis_count, 1u);
+          VisEntry e;
+          e.x = b.x, e.y = b.y, e.z = b.z;
+          e.val = val, e.slot = (uint32_t) free_slot, e.live_idx = li, e.maybe_in_image = 1u, e.pad1 = 0;
+          m.vis[vi]         = e;
+          const uint32_t qi = atomicAdd(&m.fqs->fq_count.v, 1u);
+          fq_write(m, qi, f.tag, key, val, (uint32_t) free_slot, li, vi);
+          atomicAdd(&m.ctr->blocks_new, 1ull);
+        }
+      }
+      __syncwarp();
+      return;
+    }
+    if (prev == key)
+      return; // another warp inserted the same key into the same slot first
+    // slot taken by a different key: rescan (reads now bypass L1)
+  }
+}
+
+// the reference arithmetic of the voxel -> block map, out of line: only taken outside the verified radius
+__device__ __noinline__ int voxel_to_block_cold(int v, float size, float ext) {
+  return voxel_to_block_1(v, size, ext);
+}
+
+// world -> voxel -> block of one coordinate (voxel_hash_utils.cuh:143-151 then :75-103)
+template <bool FAST>
+__device__ __forceinline__ int world_to_block_1f(float p, float size, float y_size, float ext, int shortcut_radius) {
+  if (!FAST)
+    return voxel_to_block_1(world_to_voxel_1(p, size), size, ext);
+  const float q = div_fast(p, size, y_size);
+  // q + 0.5 * sign(q): i2f(sign) * 0.5 is +-0.5, or +0 for q == +-0 (and for NaN, where it does not matter)
+  const float s = (q != 0.f) ? __uint_as_float(0x3F000000u | (__float_as_uint(q) & 0x80000000u)) : 0.f;
+  const float a = fadd(q, s);
+  // floor(a + 1e-5) for a >= 0, ceil(a - 1e-5) otherwise, then float -> int: both are the truncation of the sum
+  const int v = f2i(fadd(a, (a >= 0.f) ? 1e-5f : -1e-5f));
+  // the metric block division equals v >> 3 wherever mrh_create verified it (exhaustively, on the device)
+  if ((unsigned) (v + shortcut_radius) <= 2u * (unsigned) shortcut_radius)
+    return v >> 3;
+  return voxel_to_block_cold(v, size, ext);
+}
+
+__device__ __noinline__ float div_plain_cold(float a, float b) {
+  return fdiv(a, b);
+}
+
+// DDA set-up of allocBlocksKernel (:782-822) with the shared-reciprocal divisions
+template <bool FAST>
+__device__ __forceinline__ void dda_init_blocks(DDA& d, f3 p0, f3 p1, const MapDev& m, float y_size) {
+  if (!FAST) {
+    d.init(p0, p1, m.voxel_size, m.ext, true);
+    return;
+  }
+  const float size = m.voxel_size;
+  const f3 dir     = normalize3({fsub(p1.x, p0.x), fsub(p1.y, p0.y), fsub(p1.z, p0.z)});
+  const int R      = m.block_shortcut_radius;
+  d.cur            = {world_to_block_1f<true>(p0.x, size, y_size, m.ext[0], R), world_to_block_1f<true>(p0.y, size, y_size, m.ext[1], R), world_to_block_1f<true>(p0.z, size, y_size, m.ext[2], R)};
+  const i3 end     = {world_to_block_1f<true>(p1.x, size, y_size, m.ext[0], R), world_to_block_1f<true>(p1.y, size, y_size, m.ext[1], R), world_to_block_1f<true>(p1.z, size, y_size, m.ext[2], R)};
+  d.istep          = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
+  const float nh   = -fmul(0.5f, size);
+  const float cell = fmul(8.f, size);
+  const float big  = 3.40282346638528859812e+38f;
+  const float dirs[3] = {dir.x, dir.y, dir.z};
+  const float p0s[3]  = {p0.x, p0.y, p0.z};
+  const int curs[3]   = {d.cur.x, d.cur.y, d.cur.z};
+  const int steps[3]  = {d.istep.x, d.istep.y, d.istep.z};
+  float tm[3], td[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float bx = ffma(i2f((curs[a] + max(steps[a], 0)) * kBlockSide), size, nh);
+    const float ad = fabsf(dirs[a]);
+    if (ad < 1e-6f || fabsf(fsub(bx, dirs[a])) < 1e-6f) {
+      tm[a] = big, td[a] = big;
+    } else if (ad <= kDivHi) {
+      const float y = div_recip(ad);
+      tm[a]         = div_fast_signed(fsub(bx, p0s[a]), dirs[a], y);
+      td[a]         = div_fast_signed(fmul(i2f(steps[a]), cell), dirs[a], y);
+    } else { // not a direction any more (NaN / Inf pose): plain divisions, like the reference
+      tm[a] = div_plain_cold(fsub(bx, p0s[a]), dirs[a]);
+      td[a] = div_plain_cold(fmul(i2f(steps[a]), cell), dirs[a]);
+    }
+  }
+  d.t_max   = {tm[0], tm[1], tm[2]};
+  d.t_delta = {td[0], td[1], td[2]};
+  d.bound   = {end.x + d.istep.x, end.y + d.istep.y, end.z + d.istep.z};
+}
+
+template <int MODEL, bool FAST>
+__device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, const float* __restrict__ depth, uint32_t tile, uint32_t tiles_x, FusedSmem& sm, uint32_t tile_seq, int bulk_depth) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const int pr = lane >> 3, pc = warp * 8 + (lane & 7); // pixel inside the tile: each warp owns an 8 x 4 patch
+  const uint32_t col = tx * kTileW + pc, row = ty * kTileH + pr;
+  const bool inside  = row < cam.rows && col < cam.cols;
+  unsigned long long* set = sm.set[tile_seq & 1u];
+  sm.set[(tile_seq & 1u) ^ 1u][tid] = kNoKey; // nobody reads that one before the next tile of this CTA
+  float raw = 0.f;
+  if (bulk_depth) {
+    mbar_wait(&sm.bar_depth[tile_seq & 1u], (tile_seq >> 1) & 1u, &m.ctr->fault);
+    if (inside)
+      raw = sm.depth[tile_seq & 1u][pr][pc];
+  } else if (inside) {
+    raw = __ldg(depth + (size_t) row * cam.cols + col);
+  }
+  bool active = false;
+  DDA dda;
+  if (inside) {
+    const float d = cloud_depth(cam, row, col, raw);
+    if (d != 0.f) {
+      const float t    = truncation(m.trunc, m.trunc_scale, d);
+      const float dmin = fminf(m.max_integration_distance, fsub(d, t));
+      const float dmax = fminf(m.max_integration_distance, fadd(d, t));
+      if (!(dmin >= dmax)) {
+        const f3 p0 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmin));
+        const f3 p1 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmax));
+        dda_init_blocks<FAST>(dda, p0, p1, m, recip_of<FAST>(m.voxel_size));
+        active = true;
+      }
+    }
+  }
+  const unsigned n_rays = __popc(__ballot_sync(full, active));
+  if (lane == 0 && n_rays)
+    atomicAdd(&sm.rays, n_rays);
+  // A walk takes at most kMaxDDA steps of one cell: if both end blocks keep that distance from the
+  // border of the key range, no visited cell can leave it, and the per-step range test is skipped.
+  bool in_range = true;
+  if (active) {
+    const i3 e = {dda.bound.x - dda.istep.x, dda.bound.y - dda.istep.y, dda.bound.z - dda.istep.z};
+    in_range   = key_in_range_margin(dda.cur, kMaxDDA) && key_in_range_margin(e, kMaxDDA);
+  }
+  int iter = 0;
+  while (__any_sync(full, active)) {
+    unsigned long long key = kNoKey;
+    bool want              = false;
+    if (active) {
+      if (in_range || key_in_range(dda.cur)) {
+        key  = pack_key(dda.cur);
+        want = !set_contains(set, key);
+      } else {
+        atomicAdd(&m.ctr->dropped_table, 1ull);
+      }
+    }
+    unsigned todo = __ballot_sync(full, want);
+    while (todo) {
+      const int src               = __ffs(todo) - 1;
+      const unsigned long long kb = __shfl_sync(full, key, src);
+      todo &= ~__ballot_sync(full, want && key == kb);
+      warp_resolve(m, cam, pose, f, kb, lane);
+      if (lane == 0)
+        set_insert(set, kb);
+    }
+    __syncwarp();
+    if (active) {
+      active = dda.advance();
+      if (++iter >= kMaxDDA)
+        active = false;
+    }
+  }
+  if (lane == 0)
+    item_warp_done(m, sm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fuse role: integrateDepthMapKernel (:1095-1181) + combineVoxel (voxel_hash_utils.cuh:169-181)
+// + garbageCollectIdentify (:1674-1724) on one block
+// ---------------------------------------------------------------------------------------------
+template <bool FUSE_GC, int MODEL, bool FAST>
+__device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, const FuseEntry& e, FusedSmem& sm,
+                                          uint32_t& planes_seq, unsigned long long& cta_updated) {
+  const unsigned full = 0xFFFFFFFFu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t val = e.val;
+  if (val & 0x80000000u)
+    return; // resolution-1 blocks never reach this kernel
+  const bool stats_only = (e.key & kStatsOnly) != 0;
+  uint8_t* base         = m.pool + (size_t) val * kBlockBytes;
+  if (!stats_only && tid == 0) {
+    // every thread has left the previous item (barrier at the top of the item loop): planes[] is free
+    mbar_expect_tx(&sm.bar_planes, kBlockBytes);
+    bulk_g2s(sm.planes, base, kBlockBytes, &sm.bar_planes);
+  }
+  float min_abs  = 3.40282346638528859812e+38f;
+  uint32_t max_w = 0, n_upd = 0;
+  unsigned ok    = 0;
+  float4 sdf4    = {0.f, 0.f, 0.f, 0.f}, ss4 = {0.f, 0.f, 0.f, 0.f};
+  uint4 cw4      = {0u, 0u, 0u, 0u};
+  if (stats_only) {
+    const BlockStats st = m.stats[val];
+    min_abs = st.min_abs_sdf, max_w = st.max_weight;
+  } else {
+    // ---- pass 1: projection + depth test, registers only (the bulk copy is in flight) ----
+    const i3 b       = unpack_key(e.key & ~kStatsOnly);
+    const float size = m.voxel_size;
+    const int lx0 = (tid & 1) * 4, ly = (tid >> 1) & 7, lz = tid >> 4;
+    const float py = fmul(i2f(b.y * kBlockSide + ly), size), pz = fmul(i2f(b.z * kBlockSide + lz), size);
+    float sdf_new[4];
+    uint32_t pix[4];
+    float pcz[4], raw[4];
+    unsigned in = 0;
+    if (MODEL == 0) {
+      const float by0 = fmul(pose.Ri[1], py), by1 = fmul(pose.Ri[4], py), by2 = fmul(pose.Ri[7], py);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float px = fmul(i2f(b.x * kBlockSide + lx0 + j), size);
+        const float cx = fadd(ffma(pose.Ri[2], pz, ffma(pose.Ri[0], px, by0)), pose.ti[0]);
+        const float cy = fadd(ffma(pose.Ri[5], pz, ffma(pose.Ri[3], px, by1)), pose.ti[1]);
+        const float cz = fadd(ffma(pose.Ri[8], pz, ffma(pose.Ri[6], px, by2)), pose.ti[2]);
+        pcz[j]         = cz;
+        pix[j]         = 0;
+        // projectPoint (camera.cuh:131-160)
+        if (!(cz <= cam.min_depth) && cz <= cam.max_depth) {
+          const float y1 = recip_of<FAST>(cz);
+          const int r    = f2i(fadd(fadd(qdiv<FAST>(fmul(cam.fy, cy), cz, y1), cam.cy), 0.5f));
+          const int q    = f2i(fadd(fadd(qdiv<FAST>(fmul(cam.fx, cx), cz, y1), cam.cx), 0.5f));
+          if ((uint32_t) r < cam.rows && (uint32_t) q < cam.cols) {
+            pix[j] = (uint32_t) r * cam.cols + (uint32_t) q;
+            in |= 1u << j;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        raw[j] = (in >> j & 1u) ? __ldg(depth + pix[j]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sdf_new[j] = 0.f;
+        if (in >> j & 1u) {
+          const float d = (raw[j] <= cam.min_depth || raw[j] > cam.max_depth) ? 0.f : raw[j]; // calculateCloudKernel
+          if (d != 0.f && !(d > m.max_integration_distance)) {
+            float sdf     = fsub(d, pcz[j]);
+            const float t = truncation(m.trunc, m.trunc_scale, d);
+            if (!(sdf <= -t)) {
+              sdf_new[j] = (sdf >= 0.f) ? fminf(t, sdf) : fmaxf(-t, sdf);
+              ok |= 1u << j;
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const f3 pf = {fmul(i2f(b.x * kBlockSide + lx0 + j), size), py, pz};
+        const f3 pc = se3_mul(pose.Ri, pose.ti, pf);
+        int r, q;
+        sdf_new[j] = 0.f, pix[j] = 0;
+        if (project_point(cam, pc, r, q)) {
+          const uint32_t p = (uint32_t) r * cam.cols + (uint32_t) q;
+          const float d    = cloud_depth(cam, (uint32_t) r, (uint32_t) q, __ldg(depth + p));
+          if (d != 0.f && !(d > m.max_integration_distance)) {
+            float sdf     = fsub(d, get_depth(cam, pc));
+            const float t = truncation(m.trunc, m.trunc_scale, d);
+            if (!(sdf <= -t)) {
+              sdf_new[j] = (sdf >= 0.f) ? fminf(t, sdf) : fmaxf(-t, sdf);
+              pix[j]     = p;
+              ok |= 1u << j;
+            }
+          }
+        }
+      }
+    }
+    // colour of the pixels that will be fused (issued before the wait on the planes)
+    uint32_t pxl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pxl[j] = 0;
+      if (ok >> j & 1u) {
+        const uint8_t* p = rgb + (size_t) pix[j] * 3;
+        pxl[j]           = (uint32_t) __ldg(p) | ((uint32_t) __ldg(p + 1) << 8) | ((uint32_t) __ldg(p + 2) << 16);
+      }
+    }
+    // ---- pass 2: the block's planes are in shared memory ----
+    mbar_wait(&sm.bar_planes, planes_seq & 1u, &m.ctr->fault);
+    sdf4 = reinterpret_cast<const float4*>(sm.planes)[tid];
+    ss4  = reinterpret_cast<const float4*>(sm.planes + 512)[tid];
+    cw4  = reinterpret_cast<const uint4*>(sm.planes + 1024)[tid];
+    float* sdfv   = reinterpret_cast<float*>(&sdf4);
+    float* ssv    = reinterpret_cast<float*>(&ss4);
+    uint32_t* cwv = reinterpret_cast<uint32_t*>(&cw4);
+    const float half_size = fmul(size, 0.5f);
+    const float y_half    = recip_of<FAST>(half_size);
+    const uint32_t ws     = (uint32_t) m.weight_sample;
+    const float wsf       = __uint2float_rn(ws);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (ok >> j & 1u) {
+        const uint32_t cw = cwv[j];
+        const uint32_t w0 = cw >> 24;
+        // new voxel {sdf, weight_sample, pixel colour}; a stored voxel without weight takes the pixel colour (:1155-1166)
+        const uint32_t c0     = w0 == 0 ? pxl[j] : cw;
+        const float sdf       = sdf_new[j];
+        const float curr_mean = w0 > 0 ? sdfv[j] : sdf;
+        const float delta     = qdiv<FAST>(fsub(sdf, curr_mean), half_size, y_half);
+        const uint32_t wsum   = w0 + ws;
+        const float wsumf     = __uint2float_rn(wsum);
+        const float merged    = qdiv<FAST>(ffma(sdf, wsf, fmul(sdfv[j], __uint2float_rn(w0))), wsumf, recip_of<FAST>(wsumf));
+        // u8(0.5 c0 + 0.5 c1 + 0.5): every term is exact in float, i.e. (c0 + c1 + 1) >> 1 per channel
+        const uint32_t rgbn = __vavgu4(pxl[j], c0) & 0x00FFFFFFu;
+        const uint32_t wn   = min(wsum, (uint32_t) kWeightMax);
+        const float delta2  = qdiv<FAST>(fsub(sdf, merged), half_size, y_half);
+        float ss            = fmul(delta, delta2);
+        if (fabsf(ss) < 1.175494350822287508e-38f)
+          ss = 0.f; // ATOM.ADD.F32.FTZ of the reference flushes a denormal addend
+        sdfv[j] = merged;
+        ssv[j]  = fadd(0.f, ss); // Q1: merged_voxel starts from sum_squared = 0
+        cwv[j]  = rgbn | (wn << 24);
+        ++n_upd;
+      }
+      const uint32_t w = cwv[j] >> 24;
+      if (w != 0)
+        min_abs = fminf(min_abs, fabsf(sdfv[j]));
+      max_w = max(max_w, w);
+    }
+    planes_seq++;
+  }
+  // block-level reduction of the GC statistics (non-negative floats order like their bit patterns)
+  const uint32_t wmin = __reduce_min_sync(full, __float_as_uint(min_abs));
+  const uint32_t wmax = __reduce_max_sync(full, max_w);
+  const uint32_t wupd = __reduce_add_sync(full, n_upd);
+  if (lane == 0)
+    sm.red_min[warp] = __uint_as_float(wmin), sm.red_max[warp] = wmax, sm.red_upd[warp] = wupd;
+  __syncthreads();
+  BlockStats st;
+  st.min_abs_sdf = fminf(fminf(sm.red_min[0], sm.red_min[1]), fminf(sm.red_min[2], sm.red_min[3]));
+  st.max_weight  = max(max(sm.red_max[0], sm.red_max[1]), max(sm.red_max[2], sm.red_max[3]));
+  const bool del = FUSE_GC && gc_predicate(m, st.min_abs_sdf, st.max_weight);
+  if (tid == 0) {
+    cta_updated += sm.red_upd[0] + sm.red_upd[1] + sm.red_upd[2] + sm.red_upd[3];
+    if (del) {
+      // the block stays in the table until the finaliser: walkers of this frame must still find it
+      const uint32_t gi = atomicAdd(&m.fqs->gc_count.v, 1u);
+      m.gc_list[gi]     = {e.slot, val, e.live_idx, 0u};
+      st.min_abs_sdf    = 3.40282346638528859812e+38f;
+      st.max_weight     = 0;
+    }
+    m.stats[val] = st;
+  }
+  if (del) {
+    // deleteVoxel over the whole block (:1838-1841): free pool blocks are always all-zero
+    const float4 z = {0.f, 0.f, 0.f, 0.f};
+    reinterpret_cast<float4*>(base)[tid]                   = z;
+    reinterpret_cast<float4*>(base + kPlaneBytes)[tid]     = z;
+    reinterpret_cast<float4*>(base + 2 * kPlaneBytes)[tid] = z;
+  } else if (ok) {
+    reinterpret_cast<float4*>(base)[tid]                  = sdf4;
+    reinterpret_cast<float4*>(base + kPlaneBytes)[tid]    = ss4;
+    reinterpret_cast<uint4*>(base + 2 * kPlaneBytes)[tid] = cw4;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scheduler (thread 0): what does this CTA do next?
+// ---------------------------------------------------------------------------------------------
+struct FusedPlan {
+  uint32_t n_chunks, n_tiles, tiles_x;
+  uint32_t prefer_fuse; // 1: this CTA looks at the fusion queue before the tile queue
+  uint32_t stayer;      // 1: this CTA waits for late fusion entries; the others leave when they find nothing to claim
+};
+
+constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
+
+// Claim the next entry of the fusion queue. Tickets are handed out by fetch-and-add (a CAS loop lets
+// only one of N contenders through per L2 round trip), after a look at the two counters; a ticket
+// taken in the race window past the end of the queue stays with the CTA as `pending` until the entry
+// it names is reserved - or until production is over and it never will be.
+__device__ __forceinline__ bool claim_fuse(const MapDev& m, uint32_t& pending, uint32_t& qi) {
+  if (pending != kNoTicket) {
+    if (pending >= ld_vol(&m.fqs->fq_count.v))
+      return false;
+    qi      = pending;
+    pending = kNoTicket;
+    return true;
+  }
+  if (ld_vol(&m.fqs->q_fuse.v) >= ld_vol(&m.fqs->fq_count.v))
+    return false;
+  const uint32_t t = atomicAdd(&m.fqs->q_fuse.v, 1u);
+  if (t < ld_vol(&m.fqs->fq_count.v)) {
+    qi = t;
+    return true;
+  }
+  pending = t;
+  return false;
+}
+
+// Thread 0 of a CTA: claim the next item. chunk_open / tile_open are this CTA's knowledge that the
+// respective queue still had items the last time it looked (a queue never refills).
+struct SchedState {
+  bool chunk_open, tile_open;
+  uint32_t pending; // fusion-queue ticket waiting for its entry
+};
+
+__device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, FusedItem& it, uint32_t tile_seq, int bulk_depth, SchedState& st) {
+  FrameQueues* q = m.fqs;
+  it.kind        = kItemExit;
+  uint32_t sleep_ns = 100;
+  for (uint32_t spin = 0;; ++spin) {
+    if (spin > kSpinBound) {
+      *reinterpret_cast<volatile uint32_t*>(&m.ctr->fault) = 1u;
+      return; // exit
+    }
+    if (st.chunk_open) {
+      const uint32_t ch = atomicAdd(&q->q_chunk.v, 1u);
+      if (ch < plan.n_chunks) {
+        it.kind = kItemChunk, it.arg = ch;
+        return;
+      }
+      st.chunk_open = false;
+    }
+    uint32_t qi    = 0;
+    bool have_fuse = false;
+    if (plan.prefer_fuse || !st.tile_open)
+      have_fuse = claim_fuse(m, st.pending, qi);
+    if (!have_fuse && st.tile_open) {
+      const uint32_t t = atomicAdd(&q->q_tile.v, 1u);
+      if (t < plan.n_tiles) {
+        const uint32_t tile = f.band_lo + t;
+        it.kind = kItemTile, it.arg = tile;
+        if (bulk_depth) {
+          // depth rows of the tile -> shared memory; completes on the buffer's mbarrier. The buffer
+          // was last read two tiles of this CTA ago.
+          const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
+          const uint32_t c0 = tx * kTileW;
+          const uint32_t wb = min((uint32_t) kTileW, cam.cols - c0) * 4u;
+          const uint32_t r0 = ty * kTileH;
+          const uint32_t nr = min((uint32_t) kTileH, cam.rows - r0);
+          unsigned long long* bar = &sm.bar_depth[tile_seq & 1u];
+          mbar_expect_tx(bar, wb * nr);
+          for (uint32_t r = 0; r < nr; ++r)
+            bulk_g2s(&sm.depth[tile_seq & 1u][r][0], depth + (size_t) (r0 + r) * cam.cols + c0, wb, bar);
+        }
+        return;
+      }
+      st.tile_open = false;
+      have_fuse    = claim_fuse(m, st.pending, qi);
+    }
+    if (have_fuse) {
+      // the producer reserved this index before it wrote the entry: wait for both tagged halves
+      const char* src = reinterpret_cast<const char*>(m.fq + qi);
+      uint4 h0, h1;
+      uint32_t polls = 0;
+      do {
+        h0 = ld_vol_v4(src);
+        h1 = ld_vol_v4(src + 16);
+      } while ((h0.w != f.tag || h1.w != f.tag) && ++polls < kSpinBound);
+      if (polls >= kSpinBound) {
+        *reinterpret_cast<volatile uint32_t*>(&m.ctr->fault) = 1u;
+        return; // exit
+      }
+      it.kind = kItemFuse, it.arg = qi;
+      it.e.key  = (unsigned long long) h0.x | ((unsigned long long) h0.y << 32);
+      it.e.val  = h0.z;
+      it.e.tag0 = h0.w;
+      it.e.slot = h1.x, it.e.live_idx = h1.y, it.e.vis_idx = h1.z, it.e.tag1 = h1.w;
+      return;
+    }
+    // Nothing to claim right now. Blocks inserted by the tiles still in flight will need fusing: the
+    // stayers (one CTA slot per SM) and the holders of a pending ticket wait for them, polling words
+    // in different lines with a growing back-off; every other CTA leaves, so that a thousand pollers
+    // do not swamp the L2 slices the producers' atomics go through.
+    if (!plan.stayer && st.pending == kNoTicket)
+      return; // exit
+    if (ld_vol(&q->items_done.v) == plan.n_chunks + plan.n_tiles) {
+      // fq_count is final now (it was bumped before the producers reported their item)
+      const uint32_t cnt = ld_vol(&q->fq_count.v);
+      if (st.pending != kNoTicket ? st.pending >= cnt : ld_vol(&q->q_fuse.v) >= cnt)
+        return; // exit
+      continue;
+    }
+    __nanosleep(sleep_ns);
+    sleep_ns = min(sleep_ns * 2u, 1600u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the frame kernel
+// ---------------------------------------------------------------------------------------------
+template <bool FUSE_GC, int MODEL, bool FAST>
+__global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
+    k_frame(MapDev m, FrameDev f, CameraDev cam_arg, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, uint32_t tiles_x, int rearm, int bulk_depth, uint32_t num_sms, uint32_t pref_num, uint32_t pref_den) {
+  __shared__ FusedSmem sm;
+  // the camera model is a template parameter: with the field pinned, every `model == 0` test in the
+  // inlined camera functions folds away and the pinhole instance carries no trigonometry
+  CameraDev cam = cam_arg;
+  cam.model     = MODEL;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&sm.bar_planes, 1);
+    mbar_init(&sm.bar_depth[0], 1);
+    mbar_init(&sm.bar_depth[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    sm.last = 0, sm.warps_done = 0, sm.rays = 0;
+  }
+  sm.set[0][tid] = kNoKey;
+  sm.set[1][tid] = kNoKey;
+  cudaGridDependencySynchronize(); // chained launch: the previous frame has completed (no-op otherwise)
+  const PoseDev& pose = frame_pose(f);
+  const uint32_t n_live = m.ctr->live_count[f.live_cur];
+  FusedPlan plan;
+  plan.n_chunks    = (n_live + kFuThreads - 1) / kFuThreads;
+  plan.n_tiles     = f.band_hi - f.band_lo;
+  plan.tiles_x     = tiles_x;
+  plan.prefer_fuse = ((blockIdx.x / num_sms) % pref_den) < pref_num ? 1u : 0u;
+  plan.stayer      = blockIdx.x < num_sms ? 1u : 0u;
+  uint32_t tile_seq = 0, planes_seq = 0, iter = 0;
+  SchedState sched = {true, true, kNoTicket}; // thread 0
+  unsigned long long cta_updated = 0;
+#ifdef MRH_FUSED_DEBUG
+  unsigned long long t_prev = 0;
+  if (tid == 0) {
+    t_prev = gtimer();
+    DBG_MIN(0, t_prev); // first CTA past the dependency wait
+    DBG_MAX(1, t_prev); // last CTA past it
+  }
+#endif
+  for (;; ++iter) {
+    FusedItem& it = sm.item[iter & 1u];
+#ifdef MRH_FUSED_DEBUG
+    unsigned long long t_a = 0;
+    if (tid == 0) {
+      t_a = gtimer();
+      if (iter > 0) {
+        const int pk = sm.item[(iter & 1u) ^ 1u].kind;
+        DBG_ADD(4 + pk, t_a - t_prev); // time in role pk (thread 0's view)
+        DBG_ADD(8 + pk, 1);
+        DBG_MAX(12 + pk, t_a); // when the last item of that kind ended
+      }
+    }
+#endif
+    if (tid == 0)
+      schedule_next(m, f, cam, depth, plan, sm, it, tile_seq, bulk_depth, sched);
+#ifdef MRH_FUSED_DEBUG
+    if (tid == 0) {
+      const unsigned long long t_b = gtimer();
+      DBG_ADD(16, t_b - t_a); // time in the scheduler
+      DBG_MAX(17, t_b - t_a);
+    }
+#endif
+    __syncthreads(); // every thread has left the previous item; the next one is published
+#ifdef MRH_FUSED_DEBUG
+    if (tid == 0) {
+      t_prev = gtimer();
+    }
+#endif
+    const int kind = it.kind;
+    if (kind == kItemExit)
+      break;
+    if (kind == kItemChunk) {
+      role_chunk<FUSE_GC>(m, f, cam, pose, it.arg, n_live, sm);
+    } else if (kind == kItemTile) {
+      role_tile<MODEL, FAST>(m, f, cam, pose, depth, it.arg, tiles_x, sm, tile_seq, bulk_depth);
+      ++tile_seq;
+    } else {
+      role_fuse<FUSE_GC, MODEL, FAST>(m, f, cam, pose, depth, rgb, it.e, sm, planes_seq, cta_updated);
+    }
+  }
+  // ---- the last CTA to get here finishes the frame ----
+#ifdef MRH_FUSED_DEBUG
+  if (tid == 0) {
+    const unsigned long long t = gtimer();
+    DBG_MIN(2, t); // first CTA out of the loop
+    DBG_MAX(3, t); // last CTA out of the loop
+  }
+#endif
+  if (tid == 0) {
+    if (cta_updated)
+      atomicAdd(&m.ctr->voxels_updated, cta_updated);
+    if (sm.rays)
+      atomicAdd(&m.ctr->rays_valid, (unsigned long long) sm.rays);
+    __threadfence();
+    const unsigned done = atomicAdd(&m.fqs->done_ctas.v, 1u) + 1u;
+    sm.last             = done == gridDim.x ? 1 : 0;
+  }
+  __syncthreads();
+  if (!sm.last)
+    return;
+  __threadfence();
+  Counters* c    = m.ctr;
+  FrameQueues* q = m.fqs;
+  // deferred removal (garbageCollectFreeKernel + deleteHashEntryElement, :1727-1854): tombstone the
+  // key, push the pool block back on the free stack (appendHeapHigh :52-56), drop it from the live list
+  const uint32_t n_gc = ld_vol(&q->gc_count.v);
+  for (uint32_t i = tid; i < n_gc; i += kFuThreads) {
+    const uint4 g = ld_vol_v4(m.gc_list + i);
+    atomicExch(m.keys + g.x, kTomb);
+    const int addr   = atomicAdd(&c->heap_counter, 1);
+    m.heap[addr + 1] = g.y & 0x7FFFFFFFu;
+    m.live[f.live_cur ^ 1u][g.z].slot = kInvalid;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&c->blocks_visible, (unsigned long long) ld_vol(&c->vis_count));
+    if (n_gc)
+      atomicAdd(&c->blocks_freed, (unsigned long long) n_gc);
+#ifdef MRH_FUSED_DEBUG
+    DBG_MAX(20, gtimer()); // finaliser done
+    DBG_MAX(21, ld_vol(&q->fq_count.v));
+    DBG_MAX(22, ld_vol(&q->q_tile.v));
+#endif
+    q->q_chunk.v = 0, q->q_tile.v = 0, q->q_fuse.v = 0, q->fq_count.v = 0;
+    q->items_done.v = 0, q->gc_count.v = 0, q->done_ctas.v = 0;
+    if (rearm) {
+      c->live_count[f.live_cur] = 0; // next frame's output list
+      c->vis_count              = 0;
+      // paging trigger (GeoWrapper::compute, geowrapper.cpp:137): the host looks at these two words
+      // before the next frame, no copy engine operation and no wait involved
+      if (f.pad[0]) {
+        m.host_probe[0] = *reinterpret_cast<volatile int*>(&c->heap_counter);
+        m.host_probe[1] = (int) f.frame_index;
+        __threadfence_system();
+      }
+    }
+  }
+}
+
+} // namespace mrh

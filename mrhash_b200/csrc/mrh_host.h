@@ -114,6 +114,13 @@ struct mrh_map {
 
   uint32_t frame_index = 0; // num_integrated_frames_ (voxel_data_structures.cpp:106)
   uint32_t live_cur    = 0;
+  // fused frame kernel (mrh_fused.cuh); MRH_FRAME=split selects the two-launch frame of round 1 for A/B runs
+  bool use_fused = true, use_bulk_depth = true;
+  int fused_grid = 0, fused_ctas_per_sm = 0;
+  int fused_pref_num = 1, fused_pref_den = 4; // CTAs in slots < num of every den prefer fusion items over ray tiles
+  uint32_t fuse_tag = 0;                      // tag of the last frame's fusion-queue entries (never reset)
+  float shortcut_size = 0.f, shortcut_ext = 0.f; // parameters shortcut_radius was verified for
+  int shortcut_radius = 0;
   bool use_pdl         = true; // programmatic dependent launch of the two frame kernels (env MRH_PDL=0 switches it off)
   bool counters_clean  = true; // live_count[live_cur ^ 1] and vis_count are already zero (fast RGB-D path precondition)
   uint64_t frames_total = 0;
@@ -182,4 +189,6 @@ namespace mrh {
   int finish_gc_tail(mrh_map* m);
   FrameDev make_frame(const mrh_map* m);
   int integrate_ctas_per_sm(); // resident CTAs per SM of k_integrate as compiled (mrh_frame.cu)
+  int fused_grid(mrh_map* m);  // resident CTAs of k_frame on the whole device
+
 } // namespace mrh

@@ -39,7 +39,8 @@ struct Counters {
   uint32_t n_reintegrate;
   uint32_t n_updates;    // point-cloud path: records emitted this frame
   uint32_t carve_request; // variance path: pool blocks to split into sub-slots this frame
-  uint32_t done_ctas;     // k_integrate: CTAs that have finished (the last one re-arms the frame counters)
+  uint32_t done_ctas;     // k_integrate / k_frame: CTAs that have finished (the last one re-arms the frame counters)
+  uint32_t fault;         // a wait of the fused kernel ran into its iteration bound (never in a correct run): sticky, reported by mrh_get_stats
   // per-run totals (read back on demand)
   unsigned long long rays_valid;
   unsigned long long blocks_new;
@@ -54,6 +55,7 @@ struct Counters {
   // map state (not reset by mrh_reset_stats)
   unsigned long long low_parents;    // pool blocks carved into 64-voxel sub-slots
   unsigned long long low_live;       // live resolution-1 blocks
+  unsigned long long dbg[32];        // tuning builds only (-DMRH_FUSED_DEBUG): timers of the fused kernel
 };
 
 struct BlockStats {
@@ -77,6 +79,42 @@ struct __align__(16) VisEntry {
   uint32_t pad1;
 };
 
+// Work queues of the fused frame kernel (mrh_fused.cuh); all zero between frames. Every word sits in
+// its own 128-byte line: each is the target of thousands of atomics / polls per frame, and words that
+// share a line share one L2 atomic unit.
+struct __align__(128) QueueWord {
+  uint32_t v;
+  uint32_t pad[31];
+};
+struct FrameQueues {
+  QueueWord q_chunk;    // next chunk of the input live list (visibility role)
+  QueueWord q_tile;     // next ray tile (allocation role)
+  QueueWord q_fuse;     // next entry of the fusion queue fq[] to claim (fusion role)
+  QueueWord fq_count;   // entries reserved in fq[]
+  QueueWord items_done; // chunks + tiles completed: fq_count is final once this equals their number
+  QueueWord gc_count;   // blocks queued for removal at the end of the frame
+  QueueWord done_ctas;  // CTAs that have left the item loop (the last one finishes the frame)
+};
+
+// Entry of the fusion queue of the fused frame kernel. Producers (visibility role, allocation role)
+// reserve an index with one atomicAdd on fq_count and write the two 16-byte halves with one vector
+// store each; both halves carry the frame's tag, so a consumer that polls them knows when the entry
+// is complete without any fence (16-byte aligned vector accesses are single transactions).
+struct __align__(32) FuseEntry {
+  unsigned long long key; // packed block position; bit 63: no voxel can project into the image (stats-only entry)
+  uint32_t val;
+  uint32_t tag0;
+  uint32_t slot;
+  uint32_t live_idx;
+  uint32_t vis_idx; // position in the visible list (the starve / GC tail kernels index it)
+  uint32_t tag1;
+};
+
+// block queued for removal by the fused kernel's finaliser
+struct __align__(16) GcEntry {
+  uint32_t slot, val, live_idx, pad;
+};
+
 // record of a gathered block (same layout as mrh_dump_entry)
 struct GatherRecord {
   int x, y, z, resolution, ptr;
@@ -89,7 +127,10 @@ struct FrameDev {
   float ti[3]; // the first 24 floats have the layout of PoseDev (frame_pose)
   uint32_t frame_index;
   uint32_t live_cur; // which live list is the input of this frame
-  uint32_t pad[2];
+  uint32_t pad[2];   // pad[0]: write the paging probe at the end of this frame
+  uint32_t tag;      // fusion-queue tag of this frame (never repeats over the life of a map)
+  uint32_t band_lo, band_hi; // ray tiles [band_lo, band_hi) are walked by this rank (multi-GPU row bands)
+  uint32_t pad2;
 };
 
 struct MapDev {
@@ -105,6 +146,8 @@ struct MapDev {
   uint32_t bucket_magic; // floor(2^32 / num_buckets): block_hash_fast needs no integer division
   uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
   uint32_t shard_tag;          // shard_rank << 28: makes the starve z-buffer ids unique across ranks
+  int block_shortcut_radius;   // voxel_to_block_1(v) == v >> 3 verified for |v| <= radius (0: never take the shortcut)
+  int fast_div;                // 1: voxel size, depth range and extents allow the shared-reciprocal divisions (mrh_div.cuh)
   unsigned long long* keys;
   uint32_t* vals;
   uint32_t* heap;
@@ -114,6 +157,9 @@ struct MapDev {
   BlockStats* stats;
   LiveEntry* live[2];
   VisEntry* vis;
+  FuseEntry* fq;    // fusion queue of the fused frame kernel
+  GcEntry* gc_list; // blocks to remove at the end of the frame
+  FrameQueues* fqs; // queue words of the fused frame kernel
   VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
   unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate
   unsigned long long* zbuf;

@@ -5,11 +5,13 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 from mrhash_b200 import GeoWrapper, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 250
-w, h = 640, 480
+w = int(sys.argv[2]) if len(sys.argv) > 2 else 640
+h = int(sys.argv[3]) if len(sys.argv) > 3 else 480
+orbit = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 p = dict(synth.REPLICA_PARAMS)
 frames = []
 for k in range(n):
-    t, q, R = synth.orbit_pose(k, 1000)
+    t, q, R = synth.orbit_pose(k, orbit)
     d, c = synth.render_rgbd_torch(R, t, w, h, device="cuda")
     frames.append((t, q, d, c))
 torch.cuda.synchronize()
@@ -33,4 +35,4 @@ def run(flushed):
     return 1e3 * float(np.mean(ms)), 1e3 * float(np.median(ms)), g.getStats()
 for fl in (True, False):
     mean, med, st = run(fl)
-    print(f"{os.environ.get('MRH_LIB','default')[-20:]} CTAS/SM={os.environ.get('MRH_INTEGRATE_CTAS_PER_SM','9')} flushed={fl}: mean {mean:.1f} us median {med:.1f} us/frame  upd/frame {st['voxels_updated']/n:.0f} vis/frame {st['blocks_visible']/n:.0f}")
+    print(f"{w}x{h} {os.environ.get('MRH_LIB','default')[-20:]} frame={os.environ.get('MRH_FRAME','fused')} pref={os.environ.get('MRH_FUSED_PREF','-')} bulk={os.environ.get('MRH_BULK_DEPTH','-')} ctas={os.environ.get('MRH_FUSED_CTAS_PER_SM','-')} flushed={fl}: mean {mean:.1f} us median {med:.1f} us/frame  upd/frame {st['voxels_updated']/n:.0f} vis/frame {st['blocks_visible']/n:.0f}")
