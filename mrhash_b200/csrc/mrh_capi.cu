@@ -87,8 +87,9 @@ static int alloc_map(mrh_map* m) {
   CK(cudaMalloc(&d.live[0], sizeof(LiveEntry) * N * 2));
   CK(cudaMalloc(&d.live[1], sizeof(LiveEntry) * N * 2));
   CK(cudaMalloc(&d.vis, sizeof(VisEntry) * N * 2));
-  CK(cudaMalloc(&d.fq, sizeof(FuseEntry) * N * 2));
-  CK(cudaMemset(d.fq, 0, sizeof(FuseEntry) * N * 2)); // tag 0 is never used by a frame
+  // room for every block twice over (visible + new) plus one terminator per resident CTA
+  CK(cudaMalloc(&d.fq, sizeof(FuseEntry) * (N * 2 + 8192)));
+  CK(cudaMemset(d.fq, 0, sizeof(FuseEntry) * (N * 2 + 8192))); // tag 0 is never used by a frame
   CK(cudaMalloc(&d.gc_list, sizeof(GcEntry) * N * 2));
   CK(cudaMalloc(&d.fqs, sizeof(FrameQueues)));
   CK(cudaMemset(d.fqs, 0, sizeof(FrameQueues)));

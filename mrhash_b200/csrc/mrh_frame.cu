@@ -226,6 +226,7 @@ int fused_grid(mrh_map* m) {
     per_sm = std::min(per_sm, other);
   if (const char* e = getenv("MRH_FUSED_CTAS_PER_SM"))
     per_sm = std::max(1, std::min(per_sm, atoi(e)));
+  per_sm = std::min(per_sm, 8192 / std::max(1, m->num_sms)); // the fusion queue reserves 8192 terminator entries
   m->fused_ctas_per_sm = per_sm;
   m->fused_grid        = m->num_sms * per_sm;
   return m->fused_grid;

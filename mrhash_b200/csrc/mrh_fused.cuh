@@ -39,6 +39,7 @@ constexpr int kTileW     = 32; // one 128-byte depth row segment per bulk copy
 constexpr int kTileH     = 4;
 constexpr int kSetCells  = 128; // per-tile set of resolved block keys
 constexpr unsigned long long kStatsOnly = 1ull << 63;
+constexpr unsigned long long kTerminator = ~0ull; // fusion-queue entry that releases a waiting CTA
 
 #ifndef MRH_FUSED_MIN_CTAS
 #define MRH_FUSED_MIN_CTAS 8
@@ -120,15 +121,31 @@ struct FusedSmem {
   uint32_t red_max[kFuWarps];
   uint32_t red_upd[kFuWarps];
   uint32_t warps_done; // warps of this CTA that have finished a chunk / tile item (every 4th completes an item)
+  uint32_t n_items;    // chunks + tiles of the frame
   uint32_t rays;       // valid rays walked by this CTA
   int last;
 };
 
-// one warp of the CTA has finished its share of a chunk / tile item; the last of the four reports the item
-__device__ __forceinline__ void item_warp_done(const MapDev& m, FusedSmem& sm) {
-  const uint32_t n = atomicAdd(&sm.warps_done, 1u) + 1u;
-  if ((n & (kFuWarps - 1)) == 0)
-    atomicAdd(&m.fqs->items_done.v, 1u);
+// forward: fusion-queue writer (below)
+__device__ __forceinline__ void fq_write(const MapDev& m, uint32_t qi, uint32_t tag, unsigned long long key, uint32_t val, uint32_t slot, uint32_t live_idx, uint32_t vis_idx);
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p);
+
+// One warp of the CTA has finished its share of a chunk / tile item; the last of the four reports
+// the item. The warp that reports the LAST item of the frame knows that the fusion queue is final:
+// it appends one terminator entry per CTA, so that every CTA still waiting for a queue ticket to
+// materialise is released by the entry it is polling itself (nobody polls a shared word).
+__device__ __forceinline__ void item_warp_done(const MapDev& m, const FrameDev& f, FusedSmem& sm, int lane) {
+  uint32_t last = 0;
+  if (lane == 0) {
+    const uint32_t n = atomicAdd(&sm.warps_done, 1u) + 1u;
+    if ((n & (kFuWarps - 1)) == 0)
+      last = atomicAdd(&m.fqs->items_done.v, 1u) + 1u == sm.n_items ? 1u : 0u;
+  }
+  if (__shfl_sync(0xFFFFFFFFu, last, 0)) {
+    const uint32_t end = ld_vol(&m.fqs->fq_count.v); // every producer bumped it before reporting its item
+    for (uint32_t i = lane; i < gridDim.x; i += 32)
+      fq_write(m, end + i, f.tag, kTerminator, 0xFFFFFFFFu, 0u, 0u, 0u);
+  }
 }
 
 // division by a shared divisor: FAST = the compiler's own sequence with the reciprocal hoisted (mrh_div.cuh)
@@ -214,8 +231,7 @@ __device__ __forceinline__ void role_chunk(const MapDev& m, const FrameDev& f, c
     fq_write(m, qbase + __popc(qm & lt), f.tag, le.key | (maybe ? 0ull : kStatsOnly), le.val, slot, my_li, my_vi);
   // the counters above were bumped by atomics whose results this warp has received: whoever sees the
   // completion count sees them too (both are resolved in L2)
-  if (lane == 0)
-    item_warp_done(m, sm);
+  item_warp_done(m, f, sm, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -276,7 +292,7 @@ __device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& c
       if (bkt >= m.num_buckets)
         bkt %= m.num_buckets;
       const uint32_t slot        = bkt * kBucketSlots + (lane & 15);
-      const unsigned long long k = attempt == 0 ? m.keys[slot] : ld_cg_u64(m.keys + slot);
+      const unsigned long long k = ld_cg_u64(m.keys + slot); // the per-lane probe has used the L1 view already
       if (__ballot_sync(full, k == key)) {
         found = true;
         break;
@@ -340,80 +356,80 @@ __device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& c
   }
 }
 
-// the reference arithmetic of the voxel -> block map, out of line: only taken outside the verified radius
-__device__ __noinline__ int voxel_to_block_cold(int v, float size, float ext) {
-  return voxel_to_block_1(v, size, ext);
-}
-
-// world -> voxel -> block of one coordinate (voxel_hash_utils.cuh:143-151 then :75-103)
-template <bool FAST>
-__device__ __forceinline__ int world_to_block_1f(float p, float size, float y_size, float ext, int shortcut_radius) {
-  if (!FAST)
-    return voxel_to_block_1(world_to_voxel_1(p, size), size, ext);
-  const float q = div_fast(p, size, y_size);
-  // q + 0.5 * sign(q): i2f(sign) * 0.5 is +-0.5, or +0 for q == +-0 (and for NaN, where it does not matter)
-  const float s = (q != 0.f) ? __uint_as_float(0x3F000000u | (__float_as_uint(q) & 0x80000000u)) : 0.f;
-  const float a = fadd(q, s);
-  // floor(a + 1e-5) for a >= 0, ceil(a - 1e-5) otherwise, then float -> int: both are the truncation of the sum
-  const int v = f2i(fadd(a, (a >= 0.f) ? 1e-5f : -1e-5f));
-  // the metric block division equals v >> 3 wherever mrh_create verified it (exhaustively, on the device)
-  if ((unsigned) (v + shortcut_radius) <= 2u * (unsigned) shortcut_radius)
-    return v >> 3;
-  return voxel_to_block_cold(v, size, ext);
-}
-
-__device__ __noinline__ float div_plain_cold(float a, float b) {
-  return fdiv(a, b);
-}
-
-// DDA set-up of allocBlocksKernel (:782-822) with the shared-reciprocal divisions
-template <bool FAST>
-__device__ __forceinline__ void dda_init_blocks(DDA& d, f3 p0, f3 p1, const MapDev& m, float y_size) {
-  if (!FAST) {
-    d.init(p0, p1, m.voxel_size, m.ext, true);
-    return;
-  }
+// DDA set-up of allocBlocksKernel (:782-822) on the fast path: shared-reciprocal divisions, the integer
+// voxel -> block shortcut, no branches. Returns false when some intermediate left the range in which
+// those are exact (the caller then repeats the set-up with the reference arithmetic, DDA::init).
+__device__ __forceinline__ bool dda_init_blocks_fast(DDA& d, f3 p0, f3 p1, const MapDev& m, float y_size) {
   const float size = m.voxel_size;
   const f3 dir     = normalize3({fsub(p1.x, p0.x), fsub(p1.y, p0.y), fsub(p1.z, p0.z)});
-  const int R      = m.block_shortcut_radius;
-  d.cur            = {world_to_block_1f<true>(p0.x, size, y_size, m.ext[0], R), world_to_block_1f<true>(p0.y, size, y_size, m.ext[1], R), world_to_block_1f<true>(p0.z, size, y_size, m.ext[2], R)};
-  const i3 end     = {world_to_block_1f<true>(p1.x, size, y_size, m.ext[0], R), world_to_block_1f<true>(p1.y, size, y_size, m.ext[1], R), world_to_block_1f<true>(p1.z, size, y_size, m.ext[2], R)};
-  d.istep          = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
+  const unsigned R = (unsigned) m.block_shortcut_radius;
+  bool bad         = false;
+  // world -> voxel -> block of one coordinate (voxel_hash_utils.cuh:143-151 then :75-103)
+  auto to_block = [&](float p) -> int {
+    bad |= div_bad(p, true); // the sign of a zero quotient is absorbed by the `+ 0.5 sign(q)` below
+    const float q = div_core(p, size, y_size);
+    // q + 0.5 * sign(q): i2f(sign) * 0.5 is +-0.5, or +0 for q == +-0
+    const float s = (q != 0.f) ? __uint_as_float(0x3F000000u | (__float_as_uint(q) & 0x80000000u)) : 0.f;
+    const float a = fadd(q, s);
+    // floor(a + 1e-5) for a >= 0, ceil(a - 1e-5) otherwise, then float -> int: both are the truncation of the sum
+    const int v = f2i(fadd(a, (a >= 0.f) ? 1e-5f : -1e-5f));
+    // the metric block division equals v >> 3 wherever mrh_compute verified it (exhaustively, on the device)
+    bad |= (unsigned) v + R > 2u * R;
+    return v >> 3;
+  };
+  d.cur          = {to_block(p0.x), to_block(p0.y), to_block(p0.z)};
+  const i3 end   = {to_block(p1.x), to_block(p1.y), to_block(p1.z)};
+  d.istep        = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
   const float nh   = -fmul(0.5f, size);
   const float cell = fmul(8.f, size);
   const float big  = 3.40282346638528859812e+38f;
-  const float dirs[3] = {dir.x, dir.y, dir.z};
-  const float p0s[3]  = {p0.x, p0.y, p0.z};
-  const int curs[3]   = {d.cur.x, d.cur.y, d.cur.z};
-  const int steps[3]  = {d.istep.x, d.istep.y, d.istep.z};
-  float tm[3], td[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float bx = ffma(i2f((curs[a] + max(steps[a], 0)) * kBlockSide), size, nh);
-    const float ad = fabsf(dirs[a]);
-    if (ad < 1e-6f || fabsf(fsub(bx, dirs[a])) < 1e-6f) {
-      tm[a] = big, td[a] = big;
-    } else if (ad <= kDivHi) {
-      const float y = div_recip(ad);
-      tm[a]         = div_fast_signed(fsub(bx, p0s[a]), dirs[a], y);
-      td[a]         = div_fast_signed(fmul(i2f(steps[a]), cell), dirs[a], y);
-    } else { // not a direction any more (NaN / Inf pose): plain divisions, like the reference
-      tm[a] = div_plain_cold(fsub(bx, p0s[a]), dirs[a]);
-      td[a] = div_plain_cold(fmul(i2f(steps[a]), cell), dirs[a]);
-    }
-  }
-  d.t_max   = {tm[0], tm[1], tm[2]};
-  d.t_delta = {td[0], td[1], td[2]};
-  d.bound   = {end.x + d.istep.x, end.y + d.istep.y, end.z + d.istep.z};
+  auto axis = [&](float dr, float p, int cur, int step, float& tm, float& td) {
+    const float bx  = ffma(i2f((cur + max(step, 0)) * kBlockSide), size, nh);
+    const float ad  = fabsf(dr);
+    const bool over = ad < 1e-6f || fabsf(fsub(bx, dr)) < 1e-6f; // the reference overrides its quotients here
+    const float y   = div_recip(ad);
+    const float n1  = fsub(bx, p);
+    const uint32_t sg = __float_as_uint(dr) & 0x80000000u;
+    const float q1  = __uint_as_float(__float_as_uint(div_core(n1, ad, y)) ^ sg);
+    const float q2  = __uint_as_float(__float_as_uint(div_core(fmul(i2f(step), cell), ad, y)) ^ sg);
+    bad |= !over && (div_bad(n1, true) || !(ad <= kDivHi)); // a zero t_max is only compared and added to
+    tm = over ? big : q1;
+    td = over ? big : q2;
+  };
+  axis(dir.x, p0.x, d.cur.x, d.istep.x, d.t_max.x, d.t_delta.x);
+  axis(dir.y, p0.y, d.cur.y, d.istep.y, d.t_max.y, d.t_delta.y);
+  axis(dir.z, p0.z, d.cur.z, d.istep.z, d.t_max.z, d.t_delta.z);
+  d.bound = {end.x + d.istep.x, end.y + d.istep.y, end.z + d.istep.z};
+  return !bad;
+}
+
+// the reference arithmetic, out of line: taken by the rays the fast set-up declines
+__device__ __noinline__ DDA dda_init_blocks_ref(f3 p0, f3 p1, float size, float e0, float e1, float e2) {
+  const float ext[3] = {e0, e1, e2};
+  DDA d;
+  d.init(p0, p1, size, ext, true);
+  return d; // by value: the caller's walk state must stay in registers
+}
+
+// Per-lane presence probe: the first 32-byte sector (4 slots) of the key's home bucket. Inserts take
+// the first free slot in probe order, so at any sane load nearly every live key sits there; a miss
+// only means "ask the cooperative path". A line cached in L1 may predate an insert by another SM:
+// that, too, is only a miss.
+__device__ __forceinline__ bool quick_present(const MapDev& m, i3 b, unsigned long long key) {
+  const uint32_t h = block_hash_fast(m, b);
+  if (h < m.shard_lo || h >= m.shard_hi)
+    return true; // another GPU's block: nothing to do here
+  const ulonglong2* row = reinterpret_cast<const ulonglong2*>(m.keys + (size_t) h * kBucketSlots);
+  const ulonglong2 a = row[0], c = row[1];
+  return a.x == key || a.y == key || c.x == key || c.y == key;
 }
 
 template <int MODEL, bool FAST>
-__device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, const float* __restrict__ depth, uint32_t tile, uint32_t tiles_x, FusedSmem& sm, uint32_t tile_seq, int bulk_depth) {
+__device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, const float* __restrict__ depth, const FusedItem& it, FusedSmem& sm, uint32_t tile_seq, int bulk_depth) {
   const unsigned full = 0xFFFFFFFFu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
   const int pr = lane >> 3, pc = warp * 8 + (lane & 7); // pixel inside the tile: each warp owns an 8 x 4 patch
-  const uint32_t col = tx * kTileW + pc, row = ty * kTileH + pr;
+  const uint32_t col = it.pad[0] + pc, row = it.pad[1] + pr; // tile origin, computed once by the scheduler
   const bool inside  = row < cam.rows && col < cam.cols;
   unsigned long long* set = sm.set[tile_seq & 1u];
   sm.set[(tile_seq & 1u) ^ 1u][tid] = kNoKey; // nobody reads that one before the next tile of this CTA
@@ -436,7 +452,8 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
       if (!(dmin >= dmax)) {
         const f3 p0 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmin));
         const f3 p1 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmax));
-        dda_init_blocks<FAST>(dda, p0, p1, m, recip_of<FAST>(m.voxel_size));
+        if (!FAST || !dda_init_blocks_fast(dda, p0, p1, m, div_recip(m.voxel_size)))
+          dda = dda_init_blocks_ref(p0, p1, m.voxel_size, m.ext[0], m.ext[1], m.ext[2]);
         active = true;
       }
     }
@@ -457,8 +474,11 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
     bool want              = false;
     if (active) {
       if (in_range || key_in_range(dda.cur)) {
-        key  = pack_key(dda.cur);
-        want = !set_contains(set, key);
+        key = pack_key(dda.cur);
+        // nearly every visited block exists already: one 32-byte load per lane answers that (lanes on
+        // the same block share the transaction); the few misses are looked up in the tile's set of
+        // keys the cooperative path has dealt with
+        want = !quick_present(m, dda.cur, key) && !set_contains(set, key);
       } else {
         atomicAdd(&m.ctr->dropped_table, 1ull);
       }
@@ -471,22 +491,51 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
       warp_resolve(m, cam, pose, f, kb, lane);
       if (lane == 0)
         set_insert(set, kb);
+      __syncwarp();
     }
-    __syncwarp();
     if (active) {
       active = dda.advance();
       if (++iter >= kMaxDDA)
         active = false;
     }
   }
-  if (lane == 0)
-    item_warp_done(m, sm);
+  item_warp_done(m, f, sm, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
 // fuse role: integrateDepthMapKernel (:1095-1181) + combineVoxel (voxel_hash_utils.cuh:169-181)
 // + garbageCollectIdentify (:1674-1724) on one block
 // ---------------------------------------------------------------------------------------------
+// combineVoxel + the sum_squared update of one voxel with plain divisions (voxel_hash_utils.cuh:169-181,
+// voxel_data_structures.cu:1155-1180), out of line: the voxels whose numerators leave the window of
+// the shared-reciprocal divisions come here
+struct VoxelOut {
+  float sdf, ss;
+  uint32_t cw;
+};
+__device__ __noinline__ VoxelOut combine_ref(float sdf, float sdf0, uint32_t cw, uint32_t pxl, float half_size, uint32_t ws) {
+  const uint32_t w0     = cw >> 24;
+  const uint32_t c0     = w0 == 0 ? pxl : cw;
+  const float curr_mean = w0 > 0 ? sdf0 : sdf;
+  const float delta     = fdiv(fsub(sdf, curr_mean), half_size);
+  const uint32_t wsum   = w0 + ws;
+  const float merged    = fdiv(ffma(sdf, __uint2float_rn(ws), fmul(sdf0, __uint2float_rn(w0))), __uint2float_rn(wsum));
+  const float delta2    = fdiv(fsub(sdf, merged), half_size);
+  float ss              = fmul(delta, delta2);
+  if (fabsf(ss) < 1.175494350822287508e-38f)
+    ss = 0.f;
+  return {merged, fadd(0.f, ss), (__vavgu4(pxl, c0) & 0x00FFFFFFu) | (min(wsum, (uint32_t) kWeightMax) << 24)};
+}
+
+// projectPoint (camera.cuh:131-160) with plain divisions, out of line (same role as combine_ref)
+// returns the pixel index, or 0xFFFFFFFF when the point does not project into the image
+__device__ __noinline__ uint32_t project_ref(const CameraDev& cam, float cx, float cy, float cz) {
+  int r, q;
+  if (!project_point(cam, {cx, cy, cz}, r, q))
+    return 0xFFFFFFFFu;
+  return (uint32_t) r * cam.cols + (uint32_t) q;
+}
+
 template <bool FUSE_GC, int MODEL, bool FAST>
 __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, const CameraDev& cam, const PoseDev& pose, const float* __restrict__ depth, const uint8_t* __restrict__ rgb, const FuseEntry& e, FusedSmem& sm,
                                           uint32_t& planes_seq, unsigned long long& cta_updated) {
@@ -518,9 +567,9 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
     const float py = fmul(i2f(b.y * kBlockSide + ly), size), pz = fmul(i2f(b.z * kBlockSide + lz), size);
     float sdf_new[4];
     uint32_t pix[4];
-    float pcz[4], raw[4];
-    unsigned in = 0;
     if (MODEL == 0) {
+      float pcz[4], raw[4];
+      unsigned in = 0, bad = 0;
       const float by0 = fmul(pose.Ri[1], py), by1 = fmul(pose.Ri[4], py), by2 = fmul(pose.Ri[7], py);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -528,36 +577,48 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
         const float cx = fadd(ffma(pose.Ri[2], pz, ffma(pose.Ri[0], px, by0)), pose.ti[0]);
         const float cy = fadd(ffma(pose.Ri[5], pz, ffma(pose.Ri[3], px, by1)), pose.ti[1]);
         const float cz = fadd(ffma(pose.Ri[8], pz, ffma(pose.Ri[6], px, by2)), pose.ti[2]);
-        pcz[j]         = cz;
-        pix[j]         = 0;
-        // projectPoint (camera.cuh:131-160)
-        if (!(cz <= cam.min_depth) && cz <= cam.max_depth) {
-          const float y1 = recip_of<FAST>(cz);
-          const int r    = f2i(fadd(fadd(qdiv<FAST>(fmul(cam.fy, cy), cz, y1), cam.cy), 0.5f));
-          const int q    = f2i(fadd(fadd(qdiv<FAST>(fmul(cam.fx, cx), cz, y1), cam.cx), 0.5f));
-          if ((uint32_t) r < cam.rows && (uint32_t) q < cam.cols) {
-            pix[j] = (uint32_t) r * cam.cols + (uint32_t) q;
-            in |= 1u << j;
-          }
+        pcz[j] = cz;
+        // projectPoint (camera.cuh:131-160); the two quotients share the reciprocal of z, no branch
+        const bool zok = !(cz <= cam.min_depth) && cz <= cam.max_depth;
+        int r, q;
+        if (FAST) {
+          const float y1 = div_recip(zok ? cz : 1.f);
+          const float ay = fmul(cam.fy, cy), ax = fmul(cam.fx, cx);
+          r = f2i(fadd(fadd(div_core(ay, cz, y1), cam.cy), 0.5f));
+          q = f2i(fadd(fadd(div_core(ax, cz, y1), cam.cx), 0.5f));
+          // (a zero quotient's sign vanishes in `+ cy`)
+          if (zok && (div_bad(ay, true) || div_bad(ax, true)))
+            bad |= 1u << j;
+        } else {
+          r = f2i(fadd(fadd(fdiv(fmul(cam.fy, cy), cz), cam.cy), 0.5f));
+          q = f2i(fadd(fadd(fdiv(fmul(cam.fx, cx), cz), cam.cx), 0.5f));
         }
+        const bool inimg = zok && (uint32_t) r < cam.rows && (uint32_t) q < cam.cols;
+        pix[j] = inimg ? (uint32_t) r * cam.cols + (uint32_t) q : 0u;
+        in |= inimg ? 1u << j : 0u;
+      }
+      if (FAST && bad) { // numerators outside the division window: those voxels again, with plain divisions
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (bad >> j & 1u) {
+            const f3 pc      = se3_mul(pose.Ri, pose.ti, {fmul(i2f(b.x * kBlockSide + lx0 + j), size), py, pz});
+            const uint32_t p = project_ref(cam, pc.x, pc.y, pc.z);
+            const bool inimg = p != 0xFFFFFFFFu;
+            pix[j] = inimg ? p : 0u;
+            in     = (in & ~(1u << j)) | (inimg ? 1u << j : 0u);
+          }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         raw[j] = (in >> j & 1u) ? __ldg(depth + pix[j]) : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        sdf_new[j] = 0.f;
-        if (in >> j & 1u) {
-          const float d = (raw[j] <= cam.min_depth || raw[j] > cam.max_depth) ? 0.f : raw[j]; // calculateCloudKernel
-          if (d != 0.f && !(d > m.max_integration_distance)) {
-            float sdf     = fsub(d, pcz[j]);
-            const float t = truncation(m.trunc, m.trunc_scale, d);
-            if (!(sdf <= -t)) {
-              sdf_new[j] = (sdf >= 0.f) ? fminf(t, sdf) : fmaxf(-t, sdf);
-              ok |= 1u << j;
-            }
-          }
-        }
+        const float d = (raw[j] <= cam.min_depth || raw[j] > cam.max_depth) ? 0.f : raw[j]; // calculateCloudKernel
+        float sdf     = fsub(d, pcz[j]);
+        const float t = truncation(m.trunc, m.trunc_scale, d);
+        const bool okj = (in >> j & 1u) && d != 0.f && !(d > m.max_integration_distance) && !(sdf <= -t);
+        sdf_new[j]    = (sdf >= 0.f) ? fminf(t, sdf) : fmaxf(-t, sdf);
+        ok |= okj ? 1u << j : 0u;
       }
     } else {
 #pragma unroll 1
@@ -603,31 +664,59 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
     const float y_half    = recip_of<FAST>(half_size);
     const uint32_t ws     = (uint32_t) m.weight_sample;
     const float wsf       = __uint2float_rn(ws);
+    unsigned badc         = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      // integrateDepthMapKernel :1155-1180 + combineVoxel: new voxel {sdf, weight_sample, pixel colour};
+      // a stored voxel without weight takes the pixel colour. Computed for every voxel, kept for the ok ones.
+      const uint32_t cw     = cwv[j];
+      const uint32_t w0     = cw >> 24;
+      const uint32_t c0     = w0 == 0 ? pxl[j] : cw;
+      const float sdf       = sdf_new[j];
+      const float curr_mean = w0 > 0 ? sdfv[j] : sdf;
+      const uint32_t wsum   = w0 + ws;
+      const float wsumf     = __uint2float_rn(wsum);
+      const float n_delta   = fsub(sdf, curr_mean);
+      const float n_merged  = ffma(sdf, wsf, fmul(sdfv[j], __uint2float_rn(w0)));
+      float delta, merged, delta2, n_delta2;
+      if (FAST) {
+        delta    = div_core(n_delta, half_size, y_half);
+        merged   = div_core(n_merged, wsumf, div_recip(wsumf));
+        n_delta2 = fsub(sdf, merged);
+        delta2   = div_core(n_delta2, half_size, y_half);
+        // delta and delta2 only feed the product below, where a zero's sign is erased; merged is stored
+        if (div_bad(n_delta, true) || div_bad(n_merged, false) || div_bad(n_delta2, true))
+          badc |= 1u << j;
+      } else {
+        delta    = fdiv(n_delta, half_size);
+        merged   = fdiv(n_merged, wsumf);
+        n_delta2 = fsub(sdf, merged);
+        delta2   = fdiv(n_delta2, half_size);
+      }
+      // u8(0.5 c0 + 0.5 c1 + 0.5): every term is exact in float, i.e. (c0 + c1 + 1) >> 1 per channel
+      const uint32_t rgbn = __vavgu4(pxl[j], c0) & 0x00FFFFFFu;
+      const uint32_t wn   = min(wsum, (uint32_t) kWeightMax);
+      float ss            = fmul(delta, delta2);
+      if (fabsf(ss) < 1.175494350822287508e-38f)
+        ss = 0.f; // ATOM.ADD.F32.FTZ of the reference flushes a denormal addend
       if (ok >> j & 1u) {
-        const uint32_t cw = cwv[j];
-        const uint32_t w0 = cw >> 24;
-        // new voxel {sdf, weight_sample, pixel colour}; a stored voxel without weight takes the pixel colour (:1155-1166)
-        const uint32_t c0     = w0 == 0 ? pxl[j] : cw;
-        const float sdf       = sdf_new[j];
-        const float curr_mean = w0 > 0 ? sdfv[j] : sdf;
-        const float delta     = qdiv<FAST>(fsub(sdf, curr_mean), half_size, y_half);
-        const uint32_t wsum   = w0 + ws;
-        const float wsumf     = __uint2float_rn(wsum);
-        const float merged    = qdiv<FAST>(ffma(sdf, wsf, fmul(sdfv[j], __uint2float_rn(w0))), wsumf, recip_of<FAST>(wsumf));
-        // u8(0.5 c0 + 0.5 c1 + 0.5): every term is exact in float, i.e. (c0 + c1 + 1) >> 1 per channel
-        const uint32_t rgbn = __vavgu4(pxl[j], c0) & 0x00FFFFFFu;
-        const uint32_t wn   = min(wsum, (uint32_t) kWeightMax);
-        const float delta2  = qdiv<FAST>(fsub(sdf, merged), half_size, y_half);
-        float ss            = fmul(delta, delta2);
-        if (fabsf(ss) < 1.175494350822287508e-38f)
-          ss = 0.f; // ATOM.ADD.F32.FTZ of the reference flushes a denormal addend
         sdfv[j] = merged;
         ssv[j]  = fadd(0.f, ss); // Q1: merged_voxel starts from sum_squared = 0
         cwv[j]  = rgbn | (wn << 24);
         ++n_upd;
       }
+    }
+    badc &= ok;
+    if (FAST && badc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (badc >> j & 1u) {
+          const VoxelOut o = combine_ref(sdf_new[j], __uint_as_float(sm.planes[4 * tid + j]), sm.planes[1024 + 4 * tid + j], pxl[j], half_size, ws);
+          sdfv[j] = o.sdf, ssv[j] = o.ss, cwv[j] = o.cw;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const uint32_t w = cwv[j] >> 24;
       if (w != 0)
         min_abs = fminf(min_abs, fabsf(sdfv[j]));
@@ -676,45 +765,34 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
 struct FusedPlan {
   uint32_t n_chunks, n_tiles, tiles_x;
   uint32_t prefer_fuse; // 1: this CTA looks at the fusion queue before the tile queue
-  uint32_t stayer;      // 1: this CTA waits for late fusion entries; the others leave when they find nothing to claim
 };
 
 constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
 
-// Claim the next entry of the fusion queue. Tickets are handed out by fetch-and-add (a CAS loop lets
-// only one of N contenders through per L2 round trip), after a look at the two counters; a ticket
-// taken in the race window past the end of the queue stays with the CTA as `pending` until the entry
-// it names is reserved - or until production is over and it never will be.
-__device__ __forceinline__ bool claim_fuse(const MapDev& m, uint32_t& pending, uint32_t& qi) {
-  if (pending != kNoTicket) {
-    if (pending >= ld_vol(&m.fqs->fq_count.v))
-      return false;
-    qi      = pending;
-    pending = kNoTicket;
-    return true;
-  }
-  if (ld_vol(&m.fqs->q_fuse.v) >= ld_vol(&m.fqs->fq_count.v))
-    return false;
-  const uint32_t t = atomicAdd(&m.fqs->q_fuse.v, 1u);
-  if (t < ld_vol(&m.fqs->fq_count.v)) {
-    qi = t;
-    return true;
-  }
-  pending = t;
-  return false;
-}
-
-// Thread 0 of a CTA: claim the next item. chunk_open / tile_open are this CTA's knowledge that the
-// respective queue still had items the last time it looked (a queue never refills).
+// Scheduler state of a CTA (thread 0). Queue positions are claimed with fetch-and-add, blindly: a
+// tile index past the end closes the tile queue for this CTA; a fusion ticket names an entry that
+// may not exist yet - the CTA keeps it and polls that entry (its own 32 bytes, no shared word) until
+// the producer's tags appear: a block to fuse, or the terminator written when the last producer is done.
 struct SchedState {
-  bool chunk_open, tile_open;
-  uint32_t pending; // fusion-queue ticket waiting for its entry
+  bool chunk_open, tile_open, drained;
+  uint32_t next_tile; // tile index claimed ahead of time
+  uint32_t ticket;    // fusion-queue ticket claimed ahead of time / waiting for its entry
 };
+
+// Issued right after the item is published: the round trips of these atomics overlap the item's work.
+__device__ __forceinline__ void prefetch_claims(const MapDev& m, const FusedPlan& plan, SchedState& st) {
+  if (st.chunk_open || st.drained)
+    return;
+  if (st.tile_open && st.next_tile == kNoTicket)
+    st.next_tile = atomicAdd(&m.fqs->q_tile.v, 1u);
+  if ((plan.prefer_fuse || !st.tile_open) && st.ticket == kNoTicket)
+    st.ticket = atomicAdd(&m.fqs->q_fuse.v, 1u);
+}
 
 __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, FusedItem& it, uint32_t tile_seq, int bulk_depth, SchedState& st) {
   FrameQueues* q = m.fqs;
   it.kind        = kItemExit;
-  uint32_t sleep_ns = 100;
+  uint32_t sleep_ns = 32;
   for (uint32_t spin = 0;; ++spin) {
     if (spin > kSpinBound) {
       *reinterpret_cast<volatile uint32_t*>(&m.ctr->fault) = 1u;
@@ -728,22 +806,39 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
       }
       st.chunk_open = false;
     }
-    uint32_t qi    = 0;
-    bool have_fuse = false;
-    if (plan.prefer_fuse || !st.tile_open)
-      have_fuse = claim_fuse(m, st.pending, qi);
-    if (!have_fuse && st.tile_open) {
-      const uint32_t t = atomicAdd(&q->q_tile.v, 1u);
+    if (st.ticket != kNoTicket) {
+      // has the entry this ticket names been written? (both 16-byte halves carry the frame's tag)
+      const char* src = reinterpret_cast<const char*>(m.fq + st.ticket);
+      const uint4 h0 = ld_vol_v4(src), h1 = ld_vol_v4(src + 16);
+      if (h0.w == f.tag && h1.w == f.tag) {
+        const unsigned long long key = (unsigned long long) h0.x | ((unsigned long long) h0.y << 32);
+        const uint32_t qi            = st.ticket;
+        st.ticket                    = kNoTicket;
+        if (key == kTerminator) {
+          st.drained = true; // production is over and every real entry has a holder
+        } else {
+          it.kind = kItemFuse, it.arg = qi;
+          it.e.key = key, it.e.val = h0.z, it.e.tag0 = h0.w;
+          it.e.slot = h1.x, it.e.live_idx = h1.y, it.e.vis_idx = h1.z, it.e.tag1 = h1.w;
+          return;
+        }
+      }
+    }
+    if (st.tile_open) {
+      if (st.next_tile == kNoTicket)
+        st.next_tile = atomicAdd(&q->q_tile.v, 1u);
+      const uint32_t t = st.next_tile;
+      st.next_tile     = kNoTicket;
       if (t < plan.n_tiles) {
         const uint32_t tile = f.band_lo + t;
         it.kind = kItemTile, it.arg = tile;
+        const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
+        const uint32_t c0 = tx * kTileW, r0 = ty * kTileH;
+        it.pad[0] = c0, it.pad[1] = r0;
         if (bulk_depth) {
           // depth rows of the tile -> shared memory; completes on the buffer's mbarrier. The buffer
           // was last read two tiles of this CTA ago.
-          const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
-          const uint32_t c0 = tx * kTileW;
           const uint32_t wb = min((uint32_t) kTileW, cam.cols - c0) * 4u;
-          const uint32_t r0 = ty * kTileH;
           const uint32_t nr = min((uint32_t) kTileH, cam.rows - r0);
           unsigned long long* bar = &sm.bar_depth[tile_seq & 1u];
           mbar_expect_tx(bar, wb * nr);
@@ -753,43 +848,16 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
         return;
       }
       st.tile_open = false;
-      have_fuse    = claim_fuse(m, st.pending, qi);
+      continue;
     }
-    if (have_fuse) {
-      // the producer reserved this index before it wrote the entry: wait for both tagged halves
-      const char* src = reinterpret_cast<const char*>(m.fq + qi);
-      uint4 h0, h1;
-      uint32_t polls = 0;
-      do {
-        h0 = ld_vol_v4(src);
-        h1 = ld_vol_v4(src + 16);
-      } while ((h0.w != f.tag || h1.w != f.tag) && ++polls < kSpinBound);
-      if (polls >= kSpinBound) {
-        *reinterpret_cast<volatile uint32_t*>(&m.ctr->fault) = 1u;
-        return; // exit
-      }
-      it.kind = kItemFuse, it.arg = qi;
-      it.e.key  = (unsigned long long) h0.x | ((unsigned long long) h0.y << 32);
-      it.e.val  = h0.z;
-      it.e.tag0 = h0.w;
-      it.e.slot = h1.x, it.e.live_idx = h1.y, it.e.vis_idx = h1.z, it.e.tag1 = h1.w;
-      return;
-    }
-    // Nothing to claim right now. Blocks inserted by the tiles still in flight will need fusing: the
-    // stayers (one CTA slot per SM) and the holders of a pending ticket wait for them, polling words
-    // in different lines with a growing back-off; every other CTA leaves, so that a thousand pollers
-    // do not swamp the L2 slices the producers' atomics go through.
-    if (!plan.stayer && st.pending == kNoTicket)
+    if (st.drained)
       return; // exit
-    if (ld_vol(&q->items_done.v) == plan.n_chunks + plan.n_tiles) {
-      // fq_count is final now (it was bumped before the producers reported their item)
-      const uint32_t cnt = ld_vol(&q->fq_count.v);
-      if (st.pending != kNoTicket ? st.pending >= cnt : ld_vol(&q->q_fuse.v) >= cnt)
-        return; // exit
+    if (st.ticket == kNoTicket) {
+      st.ticket = atomicAdd(&q->q_fuse.v, 1u);
       continue;
     }
     __nanosleep(sleep_ns);
-    sleep_ns = min(sleep_ns * 2u, 1600u);
+    sleep_ns = min(sleep_ns * 2u, 512u);
   }
 }
 
@@ -823,9 +891,13 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
   plan.n_tiles     = f.band_hi - f.band_lo;
   plan.tiles_x     = tiles_x;
   plan.prefer_fuse = ((blockIdx.x / num_sms) % pref_den) < pref_num ? 1u : 0u;
-  plan.stayer      = blockIdx.x < num_sms ? 1u : 0u;
+  if (tid == 0)
+    sm.n_items = plan.n_chunks + plan.n_tiles; // (published by the first barrier of the item loop)
+  if (plan.n_chunks + plan.n_tiles == 0 && blockIdx.x == 0 && tid < 32) // nothing will ever be produced
+    for (uint32_t i = tid; i < gridDim.x; i += 32)
+      fq_write(m, i, f.tag, kTerminator, 0xFFFFFFFFu, 0u, 0u, 0u);
   uint32_t tile_seq = 0, planes_seq = 0, iter = 0;
-  SchedState sched = {true, true, kNoTicket}; // thread 0
+  SchedState sched = {true, true, false, kNoTicket, kNoTicket}; // thread 0
   unsigned long long cta_updated = 0;
 #ifdef MRH_FUSED_DEBUG
   unsigned long long t_prev = 0;
@@ -867,10 +939,12 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
     const int kind = it.kind;
     if (kind == kItemExit)
       break;
+    if (tid == 0)
+      prefetch_claims(m, plan, sched);
     if (kind == kItemChunk) {
       role_chunk<FUSE_GC>(m, f, cam, pose, it.arg, n_live, sm);
     } else if (kind == kItemTile) {
-      role_tile<MODEL, FAST>(m, f, cam, pose, depth, it.arg, tiles_x, sm, tile_seq, bulk_depth);
+      role_tile<MODEL, FAST>(m, f, cam, pose, depth, it, sm, tile_seq, bulk_depth);
       ++tile_seq;
     } else {
       role_fuse<FUSE_GC, MODEL, FAST>(m, f, cam, pose, depth, rgb, it.e, sm, planes_seq, cta_updated);
