@@ -129,7 +129,7 @@ static void free_map(mrh_map* m) {
     }
   if (m->copy_stream)
     cudaStreamDestroy(m->copy_stream);
-  cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
+  cudaFree(m->d_tile_order), cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
   cudaFreeHost(m->h_heap_probe);
@@ -613,6 +613,13 @@ extern "C" int mrh_debug_timers(mrh_map* m, unsigned long long out[32]) {
   memset(init, 0, sizeof(init));
   init[0] = init[2] = ~0ull;
   CK(cudaMemcpy((char*) m->dev.ctr + offsetof(Counters, dbg), init, sizeof(init), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int mrh_debug_trace(mrh_map* m, unsigned long long* out, size_t n_words) {
+  GUARD(m);
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(out, m->dev.reint_keys, n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

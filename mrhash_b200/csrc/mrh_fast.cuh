@@ -173,8 +173,9 @@ __global__ void k_zero_frame_counters(MapDev m, uint32_t live_out) {
   m.ctr->live_count[live_out] = 0;
   m.ctr->vis_count            = 0;
   m.ctr->done_ctas            = 0;
-  m.fqs->q_chunk.v = 0, m.fqs->q_tile.v = 0, m.fqs->q_fuse.v = 0, m.fqs->fq_count.v = 0;
-  m.fqs->items_done.v = 0, m.fqs->gc_count.v = 0, m.fqs->done_ctas.v = 0;
+  for (int i = 0; i < kQueueShards; ++i)
+    m.fqs->q_chunk[i].v = 0, m.fqs->q_tile[i].v = 0, m.fqs->q_fuse[i].v = 0;
+  m.fqs->fq_count.v = 0, m.fqs->items_done.v = 0, m.fqs->gc_count.v = 0, m.fqs->done_ctas.v = 0;
 }
 
 } // namespace mrh

@@ -42,7 +42,7 @@ constexpr unsigned long long kStatsOnly = 1ull << 63;
 constexpr unsigned long long kTerminator = ~0ull; // fusion-queue entry that releases a waiting CTA
 
 #ifndef MRH_FUSED_MIN_CTAS
-#define MRH_FUSED_MIN_CTAS 8
+#define MRH_FUSED_MIN_CTAS 7
 #endif
 
 enum : int { kItemExit = 0, kItemChunk = 1, kItemTile = 2, kItemFuse = 3 };
@@ -123,6 +123,7 @@ struct FusedSmem {
   uint32_t warps_done; // warps of this CTA that have finished a chunk / tile item (every 4th completes an item)
   uint32_t n_items;    // chunks + tiles of the frame
   uint32_t rays;       // valid rays walked by this CTA
+  alignas(16) uint4 peek[2]; // the scheduler's look at its next fusion-queue entry (cp.async target)
   int last;
 };
 
@@ -143,7 +144,8 @@ __device__ __forceinline__ void item_warp_done(const MapDev& m, const FrameDev& 
   }
   if (__shfl_sync(0xFFFFFFFFu, last, 0)) {
     const uint32_t end = ld_vol(&m.fqs->fq_count.v); // every producer bumped it before reporting its item
-    for (uint32_t i = lane; i < gridDim.x; i += 32)
+    // every CTA may hold one ticket of its class past the end of the queue
+    for (uint32_t i = lane; i < gridDim.x + kQueueShards; i += 32)
       fq_write(m, end + i, f.tag, kTerminator, 0xFFFFFFFFu, 0u, 0u, 0u);
   }
 }
@@ -331,18 +333,21 @@ __device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& c
           atomicExch(m.keys + free_slot, kTomb);
           atomicAdd(&m.ctr->dropped_heap, 1ull);
         } else {
+          // the three list reservations and the read of the free stack are independent: issued back
+          // to back they cost one L2 round trip instead of four (an insert is a chain of round trips,
+          // and the rays of the tile wait for it)
+          const uint32_t out = f.live_cur ^ 1u;
+          const uint32_t li  = atomicAdd(&m.ctr->live_count[out], 1u);
+          const uint32_t vi  = atomicAdd(&m.ctr->vis_count, 1u);
+          const uint32_t qi  = atomicAdd(&m.fqs->fq_count.v, 1u);
           const uint32_t val = m.heap[addr];
           m.stats[val]       = {3.40282346638528859812e+38f, 0u};
           m.vals[free_slot]  = val;
-          const uint32_t out = f.live_cur ^ 1u;
-          const uint32_t li  = atomicAdd(&m.ctr->live_count[out], 1u);
           m.live[out][li]    = {key, (uint32_t) free_slot, val};
-          const uint32_t vi  = atomicAdd(&m.ctr->vis_count, 1u);
           VisEntry e;
           e.x = b.x, e.y = b.y, e.z = b.z;
           e.val = val, e.slot = (uint32_t) free_slot, e.live_idx = li, e.maybe_in_image = 1u, e.pad1 = 0;
-          m.vis[vi]         = e;
-          const uint32_t qi = atomicAdd(&m.fqs->fq_count.v, 1u);
+          m.vis[vi] = e;
           fq_write(m, qi, f.tag, key, val, (uint32_t) free_slot, li, vi);
           atomicAdd(&m.ctr->blocks_new, 1ull);
         }
@@ -665,6 +670,9 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
     const uint32_t ws     = (uint32_t) m.weight_sample;
     const float wsf       = __uint2float_rn(ws);
     unsigned badc         = 0;
+    // about half of the warps of a frame have no voxel to fuse (blocks that straddle the image border or
+    // lie behind the surface): they only contribute their stored voxels to the block statistics
+    if (__any_sync(full, ok != 0)) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // integrateDepthMapKernel :1155-1180 + combineVoxel: new voxel {sdf, weight_sample, pixel colour};
@@ -714,6 +722,7 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
           const VoxelOut o = combine_ref(sdf_new[j], __uint_as_float(sm.planes[4 * tid + j]), sm.planes[1024 + 4 * tid + j], pxl[j], half_size, ws);
           sdfv[j] = o.sdf, ssv[j] = o.ss, cwv[j] = o.cw;
         }
+    }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -765,6 +774,7 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
 struct FusedPlan {
   uint32_t n_chunks, n_tiles, tiles_x;
   uint32_t prefer_fuse; // 1: this CTA looks at the fusion queue before the tile queue
+  uint32_t shard;       // queue class of this CTA
 };
 
 constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
@@ -774,19 +784,40 @@ constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
 // may not exist yet - the CTA keeps it and polls that entry (its own 32 bytes, no shared word) until
 // the producer's tags appear: a block to fuse, or the terminator written when the last producer is done.
 struct SchedState {
-  bool chunk_open, tile_open, drained;
-  uint32_t next_tile; // tile index claimed ahead of time
-  uint32_t ticket;    // fusion-queue ticket claimed ahead of time / waiting for its entry
+  bool chunk_open, tile_open, drained, peeked;
+  uint32_t next_chunk; // chunk index assigned / claimed ahead of time
+  uint32_t next_tile;  // tile index assigned / claimed ahead of time
+  uint32_t ticket;     // fusion-queue ticket assigned / claimed ahead of time, waiting for its entry
 };
 
+// The first item of each queue is assigned statically (CTA c of class s = c % kQueueShards, rank
+// r = c / kQueueShards, owns index s + kQueueShards * r): a frame starts without a single round trip
+// to a queue head. Later claims continue behind the statically assigned ones.
+__device__ __forceinline__ uint32_t shard_base(uint32_t shard) {
+  return (gridDim.x - shard + kQueueShards - 1) / kQueueShards; // CTAs in this class
+}
+__device__ __forceinline__ uint32_t claim(QueueWord* heads, uint32_t shard) {
+  return shard + kQueueShards * (shard_base(shard) + atomicAdd(&heads[shard].v, 1u));
+}
+
 // Issued right after the item is published: the round trips of these atomics overlap the item's work.
-__device__ __forceinline__ void prefetch_claims(const MapDev& m, const FusedPlan& plan, SchedState& st) {
-  if (st.chunk_open || st.drained)
+__device__ __forceinline__ void prefetch_claims(const MapDev& m, const FusedPlan& plan, FusedSmem& sm, SchedState& st) {
+  if (st.drained)
     return;
   if (st.tile_open && st.next_tile == kNoTicket)
-    st.next_tile = atomicAdd(&m.fqs->q_tile.v, 1u);
-  if ((plan.prefer_fuse || !st.tile_open) && st.ticket == kNoTicket)
-    st.ticket = atomicAdd(&m.fqs->q_fuse.v, 1u);
+    st.next_tile = claim(m.fqs->q_tile, plan.shard);
+  if (st.ticket == kNoTicket) {
+    if (plan.prefer_fuse || !st.tile_open)
+      st.ticket = plan.shard + kQueueShards * atomicAdd(&m.fqs->q_fuse[plan.shard].v, 1u);
+  } else {
+    // look at the entry the ticket names while the item runs: two 16-byte asynchronous copies
+    // (L2 -> shared memory, no registers held) are in flight during it
+    const char* src = reinterpret_cast<const char*>(m.fq + st.ticket);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&sm.peek[0])), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&sm.peek[1])), "l"(src + 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    st.peeked = true;
+  }
 }
 
 __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, FusedItem& it, uint32_t tile_seq, int bulk_depth, SchedState& st) {
@@ -799,7 +830,10 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
       return; // exit
     }
     if (st.chunk_open) {
-      const uint32_t ch = atomicAdd(&q->q_chunk.v, 1u);
+      if (st.next_chunk == kNoTicket)
+        st.next_chunk = claim(q->q_chunk, plan.shard);
+      const uint32_t ch = st.next_chunk;
+      st.next_chunk     = kNoTicket;
       if (ch < plan.n_chunks) {
         it.kind = kItemChunk, it.arg = ch;
         return;
@@ -809,7 +843,15 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
     if (st.ticket != kNoTicket) {
       // has the entry this ticket names been written? (both 16-byte halves carry the frame's tag)
       const char* src = reinterpret_cast<const char*>(m.fq + st.ticket);
-      const uint4 h0 = ld_vol_v4(src), h1 = ld_vol_v4(src + 16);
+      uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+      if (st.peeked) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        const volatile uint32_t* pk = reinterpret_cast<const volatile uint32_t*>(sm.peek);
+        h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        st.peeked = false;
+      }
+      if (h0.w != f.tag || h1.w != f.tag)
+        h0 = ld_vol_v4(src), h1 = ld_vol_v4(src + 16);
       if (h0.w == f.tag && h1.w == f.tag) {
         const unsigned long long key = (unsigned long long) h0.x | ((unsigned long long) h0.y << 32);
         const uint32_t qi            = st.ticket;
@@ -826,11 +868,13 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
     }
     if (st.tile_open) {
       if (st.next_tile == kNoTicket)
-        st.next_tile = atomicAdd(&q->q_tile.v, 1u);
+        st.next_tile = claim(q->q_tile, plan.shard);
       const uint32_t t = st.next_tile;
       st.next_tile     = kNoTicket;
       if (t < plan.n_tiles) {
-        const uint32_t tile = f.band_lo + t;
+        // border-first order (tile_order, built by the host): blocks enter the map where new surface
+        // enters the image, and an insert is a chain of L2 round trips - those tiles start first
+        const uint32_t tile = m.tile_order[f.band_lo + t];
         it.kind = kItemTile, it.arg = tile;
         const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
         const uint32_t c0 = tx * kTileW, r0 = ty * kTileH;
@@ -853,7 +897,7 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
     if (st.drained)
       return; // exit
     if (st.ticket == kNoTicket) {
-      st.ticket = atomicAdd(&q->q_fuse.v, 1u);
+      st.ticket = plan.shard + kQueueShards * atomicAdd(&q->q_fuse[plan.shard].v, 1u);
       continue;
     }
     __nanosleep(sleep_ns);
@@ -891,13 +935,17 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
   plan.n_tiles     = f.band_hi - f.band_lo;
   plan.tiles_x     = tiles_x;
   plan.prefer_fuse = ((blockIdx.x / num_sms) % pref_den) < pref_num ? 1u : 0u;
+  plan.shard       = blockIdx.x % kQueueShards;
   if (tid == 0)
     sm.n_items = plan.n_chunks + plan.n_tiles; // (published by the first barrier of the item loop)
   if (plan.n_chunks + plan.n_tiles == 0 && blockIdx.x == 0 && tid < 32) // nothing will ever be produced
-    for (uint32_t i = tid; i < gridDim.x; i += 32)
+    for (uint32_t i = tid; i < gridDim.x + kQueueShards; i += 32)
       fq_write(m, i, f.tag, kTerminator, 0xFFFFFFFFu, 0u, 0u, 0u);
   uint32_t tile_seq = 0, planes_seq = 0, iter = 0;
-  SchedState sched = {true, true, false, kNoTicket, kNoTicket}; // thread 0
+  SchedState sched; // thread 0
+  sched.chunk_open = true, sched.tile_open = true, sched.drained = false, sched.peeked = false;
+  sched.next_chunk = blockIdx.x, sched.next_tile = blockIdx.x, sched.ticket = kNoTicket;
+
   unsigned long long cta_updated = 0;
 #ifdef MRH_FUSED_DEBUG
   unsigned long long t_prev = 0;
@@ -915,7 +963,15 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
       t_a = gtimer();
       if (iter > 0) {
         const int pk = sm.item[(iter & 1u) ^ 1u].kind;
+        if (blockIdx.x % 37 == 0) { // timeline of a sample of CTAs: {cta, kind, item begin, item end (thread 0)}
+          const unsigned long long ti = atomicAdd(&m.ctr->dbg[30], 1ull);
+          if (ti < 8192) {
+            m.reint_keys[2 * ti]     = ((unsigned long long) blockIdx.x << 32) | (unsigned) pk;
+            m.reint_keys[2 * ti + 1] = ((t_prev & 0xFFFFFFFFull) << 32) | (t_a & 0xFFFFFFFFull);
+          }
+        }
         DBG_ADD(4 + pk, t_a - t_prev); // time in role pk (thread 0's view)
+        DBG_MAX(24 + pk, t_a - t_prev); // longest item of that kind
         DBG_ADD(8 + pk, 1);
         DBG_MAX(12 + pk, t_a); // when the last item of that kind ended
       }
@@ -940,7 +996,7 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
     if (kind == kItemExit)
       break;
     if (tid == 0)
-      prefetch_claims(m, plan, sched);
+      prefetch_claims(m, plan, sm, sched);
     if (kind == kItemChunk) {
       role_chunk<FUSE_GC>(m, f, cam, pose, it.arg, n_live, sm);
     } else if (kind == kItemTile) {
@@ -991,10 +1047,11 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
 #ifdef MRH_FUSED_DEBUG
     DBG_MAX(20, gtimer()); // finaliser done
     DBG_MAX(21, ld_vol(&q->fq_count.v));
-    DBG_MAX(22, ld_vol(&q->q_tile.v));
+    DBG_MAX(22, ld_vol(&q->q_tile[0].v));
 #endif
-    q->q_chunk.v = 0, q->q_tile.v = 0, q->q_fuse.v = 0, q->fq_count.v = 0;
-    q->items_done.v = 0, q->gc_count.v = 0, q->done_ctas.v = 0;
+    for (int i = 0; i < kQueueShards; ++i)
+      q->q_chunk[i].v = 0, q->q_tile[i].v = 0, q->q_fuse[i].v = 0;
+    q->fq_count.v = 0, q->items_done.v = 0, q->gc_count.v = 0, q->done_ctas.v = 0;
     if (rearm) {
       c->live_count[f.live_cur] = 0; // next frame's output list
       c->vis_count              = 0;

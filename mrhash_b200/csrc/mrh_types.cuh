@@ -86,10 +86,14 @@ struct __align__(128) QueueWord {
   uint32_t v;
   uint32_t pad[31];
 };
+// Queue heads come in kQueueShards classes: item i belongs to class i % kQueueShards, CTA c claims from
+// class c % kQueueShards only. L2 serves returning atomics on ONE address one at a time (~5 ns each
+// under contention): a single head per queue throttled the hand-out of a frame's ~4 500 items to ~20 us.
+constexpr int kQueueShards = 16;
 struct FrameQueues {
-  QueueWord q_chunk;    // next chunk of the input live list (visibility role)
-  QueueWord q_tile;     // next ray tile (allocation role)
-  QueueWord q_fuse;     // next entry of the fusion queue fq[] to claim (fusion role)
+  QueueWord q_chunk[kQueueShards]; // next chunk of the input live list (visibility role), per class
+  QueueWord q_tile[kQueueShards];  // next ray tile (allocation role), per class
+  QueueWord q_fuse[kQueueShards];  // next entry of the fusion queue fq[] to claim (fusion role), per class
   QueueWord fq_count;   // entries reserved in fq[]
   QueueWord items_done; // chunks + tiles completed: fq_count is final once this equals their number
   QueueWord gc_count;   // blocks queued for removal at the end of the frame
@@ -160,6 +164,7 @@ struct MapDev {
   FuseEntry* fq;    // fusion queue of the fused frame kernel
   GcEntry* gc_list; // blocks to remove at the end of the frame
   FrameQueues* fqs; // queue words of the fused frame kernel
+  const uint32_t* tile_order; // ray tiles of the fused kernel, image border first
   VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
   unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate
   unsigned long long* zbuf;

@@ -33,6 +33,19 @@ for k in range(n):
         print(f"frame {k}: last CTA start +{us(v[1]):.1f} us | first/last CTA out of loop +{us(v[2]):.1f}/+{us(v[3]):.1f} | finaliser +{us(v[20]):.1f} | fq {v[21]} q_tile {v[22]}")
         for r in (1, 2, 3):
             cnt = max(v[8 + r], 1)
-            print(f"   {names[r]:5s}: items {v[8+r]:6d} sum {v[4+r]/1e3:9.1f} us  mean {v[4+r]/cnt/1e3:7.2f} us  last ended +{us(v[12+r]):.1f} us")
+            print(f"   {names[r]:5s}: items {v[8+r]:6d} sum {v[4+r]/1e3:9.1f} us  mean {v[4+r]/cnt/1e3:7.2f} us  last ended +{us(v[12+r]):.1f} us  longest {v[24+r]/1e3:.1f} us")
         print(f"   sched: sum {v[16]/1e3:.1f} us max {v[17]/1e3:.1f} us")
+    if k == n - 1:
+        ntr = min(int(v[30]), 8192)
+        tb = (C.c_uint64 * (2 * ntr))()
+        lib.mrh_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]
+        lib.mrh_debug_trace(g._h, tb, 2 * ntr)
+        t0l = t0 & 0xFFFFFFFF
+        rows = {}
+        for i in range(ntr):
+            cta, kind = tb[2 * i] >> 32, tb[2 * i] & 0xFF
+            a, b = tb[2 * i + 1] >> 32, tb[2 * i + 1] & 0xFFFFFFFF
+            rows.setdefault(cta, []).append((((a - t0l) & 0xFFFFFFFF) / 1e3, ((b - t0l) & 0xFFFFFFFF) / 1e3, names.get(kind, "?")))
+        for cta in sorted(rows)[:40]:
+            print(f"cta {cta:5d}: " + " ".join(f"{nm[0]}[{a:.1f}-{b:.1f}]" for a, b, nm in sorted(rows[cta])))
 print(g.getStats())
