@@ -129,7 +129,7 @@ static void free_map(mrh_map* m) {
     }
   if (m->copy_stream)
     cudaStreamDestroy(m->copy_stream);
-  cudaFree(m->d_tile_order), cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
+  cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
   cudaFreeHost(m->h_heap_probe);

@@ -215,32 +215,6 @@ namespace {
   }
 } // namespace
 
-// Ray tiles sorted by their distance to the image border (stable, so neighbours stay neighbours).
-static int build_tile_order(mrh_map* m, uint32_t tiles_x, uint32_t tiles_y) {
-  const CameraDev& k = m->cam;
-  if (m->d_tile_order && m->tile_order_rows == k.rows && m->tile_order_cols == k.cols)
-    return 0;
-  const uint32_t n = tiles_x * tiles_y;
-  std::vector<uint32_t> order(n);
-  for (uint32_t i = 0; i < n; ++i)
-    order[i] = i;
-  auto dist = [&](uint32_t t) {
-    const int c0 = (int) (t % tiles_x) * kTileW, r0 = (int) (t / tiles_x) * kTileH;
-    const int dc = std::min(c0, std::max(0, (int) k.cols - (c0 + kTileW)));
-    const int dr = std::min(r0, std::max(0, (int) k.rows - (r0 + kTileH)));
-    return std::min(dc, dr);
-  };
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dist(a) < dist(b); });
-  cudaStreamSynchronize(m->stream); // no frame may still be reading the old table
-  cudaFree(m->d_tile_order);
-  m->d_tile_order = nullptr;
-  if (cudaMalloc(&m->d_tile_order, sizeof(uint32_t) * n) != cudaSuccess || cudaMemcpy(m->d_tile_order, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice) != cudaSuccess)
-    return fail("out of device memory for the tile order (%u tiles)", n);
-  m->tile_order_rows = k.rows, m->tile_order_cols = k.cols;
-  m->dev.tile_order  = m->d_tile_order;
-  return 0;
-}
-
 // resident CTAs of the fused kernel on the whole device (every instance is compiled for the same bound)
 int fused_grid(mrh_map* m) {
   if (m->fused_grid > 0)
@@ -279,8 +253,6 @@ int integrate_rgbd(mrh_map* m) {
     }
     const uint32_t tiles_x = (k.cols + kTileW - 1) / kTileW, tiles_y = (k.rows + kTileH - 1) / kTileH;
     const int rearm        = c.starve ? 0 : 1;
-    if (build_tile_order(m, tiles_x, tiles_y))
-      return 1;
     FrameDev ff            = f;
     ff.tag                 = ++m->fuse_tag;
     ff.band_lo             = 0;

@@ -362,14 +362,14 @@ __device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& c
 }
 
 // DDA set-up of allocBlocksKernel (:782-822) on the fast path: shared-reciprocal divisions, the integer
-// voxel -> block shortcut, no branches. Returns false when some intermediate left the range in which
-// those are exact (the caller then repeats the set-up with the reference arithmetic, DDA::init).
-__device__ __forceinline__ bool dda_init_blocks_fast(DDA& d, f3 p0, f3 p1, const MapDev& m, float y_size) {
+// voxel -> block shortcut, no branches; in two stages so that a patch whose rays cannot reach an
+// unallocated block stops after the first.
+// Stage A: the blocks of the two ray ends (world -> voxel -> block, voxel_hash_utils.cuh:143-151 then
+// :75-103). Returns false when an intermediate left the range in which the shortcuts are exact.
+__device__ __forceinline__ bool ray_end_blocks_fast(f3 p0, f3 p1, const MapDev& m, float y_size, i3& cur, i3& end) {
   const float size = m.voxel_size;
-  const f3 dir     = normalize3({fsub(p1.x, p0.x), fsub(p1.y, p0.y), fsub(p1.z, p0.z)});
   const unsigned R = (unsigned) m.block_shortcut_radius;
   bool bad         = false;
-  // world -> voxel -> block of one coordinate (voxel_hash_utils.cuh:143-151 then :75-103)
   auto to_block = [&](float p) -> int {
     bad |= div_bad(p, true); // the sign of a zero quotient is absorbed by the `+ 0.5 sign(q)` below
     const float q = div_core(p, size, y_size);
@@ -382,14 +382,22 @@ __device__ __forceinline__ bool dda_init_blocks_fast(DDA& d, f3 p0, f3 p1, const
     bad |= (unsigned) v + R > 2u * R;
     return v >> 3;
   };
-  d.cur          = {to_block(p0.x), to_block(p0.y), to_block(p0.z)};
-  const i3 end   = {to_block(p1.x), to_block(p1.y), to_block(p1.z)};
-  d.istep        = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
+  cur = {to_block(p0.x), to_block(p0.y), to_block(p0.z)};
+  end = {to_block(p1.x), to_block(p1.y), to_block(p1.z)};
+  return !bad;
+}
+// Stage B: direction, step signs, t_max / t_delta. Returns false like stage A.
+__device__ __forceinline__ bool dda_steps_fast(DDA& d, f3 p0, f3 p1, i3 cur, i3 end, const MapDev& m) {
+  const float size = m.voxel_size;
+  const f3 dir     = normalize3({fsub(p1.x, p0.x), fsub(p1.y, p0.y), fsub(p1.z, p0.z)});
+  bool bad         = false;
+  d.cur            = cur;
+  d.istep          = {sign_i(dir.x), sign_i(dir.y), sign_i(dir.z)};
   const float nh   = -fmul(0.5f, size);
   const float cell = fmul(8.f, size);
   const float big  = 3.40282346638528859812e+38f;
-  auto axis = [&](float dr, float p, int cur, int step, float& tm, float& td) {
-    const float bx  = ffma(i2f((cur + max(step, 0)) * kBlockSide), size, nh);
+  auto axis = [&](float dr, float p, int c, int step, float& tm, float& td) {
+    const float bx  = ffma(i2f((c + max(step, 0)) * kBlockSide), size, nh);
     const float ad  = fabsf(dr);
     const bool over = ad < 1e-6f || fabsf(fsub(bx, dr)) < 1e-6f; // the reference overrides its quotients here
     const float y   = div_recip(ad);
@@ -401,9 +409,9 @@ __device__ __forceinline__ bool dda_init_blocks_fast(DDA& d, f3 p0, f3 p1, const
     tm = over ? big : q1;
     td = over ? big : q2;
   };
-  axis(dir.x, p0.x, d.cur.x, d.istep.x, d.t_max.x, d.t_delta.x);
-  axis(dir.y, p0.y, d.cur.y, d.istep.y, d.t_max.y, d.t_delta.y);
-  axis(dir.z, p0.z, d.cur.z, d.istep.z, d.t_max.z, d.t_delta.z);
+  axis(dir.x, p0.x, cur.x, d.istep.x, d.t_max.x, d.t_delta.x);
+  axis(dir.y, p0.y, cur.y, d.istep.y, d.t_max.y, d.t_delta.y);
+  axis(dir.z, p0.z, cur.z, d.istep.z, d.t_max.z, d.t_delta.z);
   d.bound = {end.x + d.istep.x, end.y + d.istep.y, end.z + d.istep.z};
   return !bad;
 }
@@ -447,7 +455,7 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
     raw = __ldg(depth + (size_t) row * cam.cols + col);
   }
   bool active = false;
-  DDA dda;
+  f3 p0 = {0.f, 0.f, 0.f}, p1 = p0;
   if (inside) {
     const float d = cloud_depth(cam, row, col, raw);
     if (d != 0.f) {
@@ -455,13 +463,63 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
       const float dmin = fminf(m.max_integration_distance, fsub(d, t));
       const float dmax = fminf(m.max_integration_distance, fadd(d, t));
       if (!(dmin >= dmax)) {
-        const f3 p0 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmin));
-        const f3 p1 = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmax));
-        if (!FAST || !dda_init_blocks_fast(dda, p0, p1, m, div_recip(m.voxel_size)))
-          dda = dda_init_blocks_ref(p0, p1, m.voxel_size, m.ext[0], m.ext[1], m.ext[2]);
+        p0     = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmin));
+        p1     = se3_mul(pose.R, pose.t, inverse_projection(cam, row, col, dmax));
         active = true;
       }
     }
+  }
+  DDA dda;
+  if (FAST) {
+    // ---- can any ray of this warp's 8 x 4 patch reach a block that does not exist yet? ----
+    // On every axis a walk moves monotonically from its start block towards its end block and stops
+    // there at the latest (allocBlocksKernel :826-854), so every block a ray visits lies inside the
+    // box spanned by its two end blocks, and every block the patch visits inside the union box of
+    // its rays. That box is a handful of blocks (the rays of a patch are nearly parallel): one lane
+    // per block looks it up with the per-lane probe; if all exist, nothing can be inserted and the
+    // whole stepping set-up and walk of the patch is skipped. Any doubt (a ray off the fast path, a
+    // box larger than 4 x 4 x 2, a block not found in the first sector of its bucket) falls back to
+    // the walk, which is exact.
+    i3 cur = {0, 0, 0}, end = {0, 0, 0};
+    const bool fast_ok = !active || ray_end_blocks_fast(p0, p1, m, div_recip(m.voxel_size), cur, end);
+    const int big_i    = 0x3FFFFFFF;
+    const int lox = __reduce_min_sync(full, active ? min(cur.x, end.x) : big_i), hix = __reduce_max_sync(full, active ? max(cur.x, end.x) : -big_i);
+    const int loy = __reduce_min_sync(full, active ? min(cur.y, end.y) : big_i), hiy = __reduce_max_sync(full, active ? max(cur.y, end.y) : -big_i);
+    const int loz = __reduce_min_sync(full, active ? min(cur.z, end.z) : big_i), hiz = __reduce_max_sync(full, active ? max(cur.z, end.z) : -big_i);
+    const bool all_fast = __all_sync(full, fast_ok);
+    bool skip           = hix < lox; // no active ray at all
+    if (!skip && all_fast) {
+      const unsigned nx = (unsigned) (hix - lox) + 1u, ny = (unsigned) (hiy - loy) + 1u, nz = (unsigned) (hiz - loz) + 1u;
+      // lanes enumerate a 4 x 4 x 2 box; the axis with at most two blocks takes the 1-bit coordinate
+      const unsigned a = lane & 3, b = (lane >> 2) & 3, c = lane >> 4;
+      unsigned ix, iy, iz;
+      bool fits;
+      if (nz <= 2u)
+        ix = a, iy = b, iz = c, fits = nx <= 4u && ny <= 4u;
+      else if (ny <= 2u)
+        ix = a, iz = b, iy = c, fits = nx <= 4u && nz <= 4u;
+      else
+        iy = a, iz = b, ix = c, fits = nx <= 2u && ny <= 4u && nz <= 4u;
+      if (fits) {
+        bool present = true;
+        if (ix < nx && iy < ny && iz < nz) {
+          const i3 bb = {lox + (int) ix, loy + (int) iy, loz + (int) iz};
+          present     = key_in_range(bb) && quick_present(m, bb, pack_key(bb));
+        }
+        skip = __all_sync(full, present);
+      }
+    }
+    if (skip) {
+      const unsigned n_skipped = __popc(__ballot_sync(full, active));
+      if (lane == 0 && n_skipped)
+        atomicAdd(&sm.rays, n_skipped);
+      item_warp_done(m, f, sm, lane);
+      return;
+    }
+    if (active && !(fast_ok && dda_steps_fast(dda, p0, p1, cur, end, m)))
+      dda = dda_init_blocks_ref(p0, p1, m.voxel_size, m.ext[0], m.ext[1], m.ext[2]);
+  } else if (active) {
+    dda = dda_init_blocks_ref(p0, p1, m.voxel_size, m.ext[0], m.ext[1], m.ext[2]);
   }
   const unsigned n_rays = __popc(__ballot_sync(full, active));
   if (lane == 0 && n_rays)
@@ -785,8 +843,11 @@ constexpr uint32_t kNoTicket = 0xFFFFFFFFu;
 // the producer's tags appear: a block to fuse, or the terminator written when the last producer is done.
 struct SchedState {
   bool chunk_open, tile_open, drained, peeked;
+  bool a_issued;       // the depth rows of tile_a are on their way into shared memory
   uint32_t next_chunk; // chunk index assigned / claimed ahead of time
-  uint32_t next_tile;  // tile index assigned / claimed ahead of time
+  uint32_t tile_a;     // the next tile of this CTA (assigned, or claimed two items ago)
+  uint32_t tile_b;     // the one after it (claim in flight)
+  uint32_t a_c0, a_r0; // pixel origin of tile_a
   uint32_t ticket;     // fusion-queue ticket assigned / claimed ahead of time, waiting for its entry
 };
 
@@ -800,12 +861,38 @@ __device__ __forceinline__ uint32_t claim(QueueWord* heads, uint32_t shard) {
   return shard + kQueueShards * (shard_base(shard) + atomicAdd(&heads[shard].v, 1u));
 }
 
-// Issued right after the item is published: the round trips of these atomics overlap the item's work.
-__device__ __forceinline__ void prefetch_claims(const MapDev& m, const FusedPlan& plan, FusedSmem& sm, SchedState& st) {
+// depth rows of a tile -> shared memory (cp.async.bulk, one 128-byte row segment per copy); completes
+// on the buffer's mbarrier. `seq` = how many tiles this CTA has walked before this one: the buffer and
+// its barrier alternate, and buffer seq & 1 was last read two tiles ago.
+__device__ __forceinline__ void issue_depth(const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, SchedState& st, uint32_t seq, int bulk_depth) {
+  const uint32_t tile = f.band_lo + st.tile_a;
+  const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
+  const uint32_t c0 = tx * kTileW, r0 = ty * kTileH;
+  st.a_c0 = c0, st.a_r0 = r0, st.a_issued = true;
+  if (bulk_depth) {
+    const uint32_t wb = min((uint32_t) kTileW, cam.cols - c0) * 4u;
+    const uint32_t nr = min((uint32_t) kTileH, cam.rows - r0);
+    unsigned long long* bar = &sm.bar_depth[seq & 1u];
+    mbar_expect_tx(bar, wb * nr);
+    for (uint32_t r = 0; r < nr; ++r)
+      bulk_g2s(&sm.depth[seq & 1u][r][0], depth + (size_t) (r0 + r) * cam.cols + c0, wb, bar);
+  }
+}
+
+// Issued right after the item is published: the round trips of these claims, and the transfer of the
+// NEXT tile's depth rows, overlap the item's work. Tile claims run two items ahead, so that the index
+// of the next tile is known here (next_seq: the tile sequence number that tile will have).
+__device__ __forceinline__ void prefetch_claims(const MapDev& m, const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, SchedState& st, uint32_t next_seq, int bulk_depth) {
   if (st.drained)
     return;
-  if (st.tile_open && st.next_tile == kNoTicket)
-    st.next_tile = claim(m.fqs->q_tile, plan.shard);
+  if (st.tile_open) {
+    if (st.tile_a == kNoTicket)
+      st.tile_a = st.tile_b, st.tile_b = kNoTicket, st.a_issued = false;
+    if (st.tile_b == kNoTicket)
+      st.tile_b = claim(m.fqs->q_tile, plan.shard);
+    if (st.tile_a != kNoTicket && !st.a_issued && st.tile_a < plan.n_tiles)
+      issue_depth(f, cam, depth, plan, sm, st, next_seq, bulk_depth);
+  }
   if (st.ticket == kNoTicket) {
     if (plan.prefer_fuse || !st.tile_open)
       st.ticket = plan.shard + kQueueShards * atomicAdd(&m.fqs->q_fuse[plan.shard].v, 1u);
@@ -867,28 +954,17 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
       }
     }
     if (st.tile_open) {
-      if (st.next_tile == kNoTicket)
-        st.next_tile = claim(q->q_tile, plan.shard);
-      const uint32_t t = st.next_tile;
-      st.next_tile     = kNoTicket;
-      if (t < plan.n_tiles) {
-        // border-first order (tile_order, built by the host): blocks enter the map where new surface
-        // enters the image, and an insert is a chain of L2 round trips - those tiles start first
-        const uint32_t tile = m.tile_order[f.band_lo + t];
-        it.kind = kItemTile, it.arg = tile;
-        const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
-        const uint32_t c0 = tx * kTileW, r0 = ty * kTileH;
-        it.pad[0] = c0, it.pad[1] = r0;
-        if (bulk_depth) {
-          // depth rows of the tile -> shared memory; completes on the buffer's mbarrier. The buffer
-          // was last read two tiles of this CTA ago.
-          const uint32_t wb = min((uint32_t) kTileW, cam.cols - c0) * 4u;
-          const uint32_t nr = min((uint32_t) kTileH, cam.rows - r0);
-          unsigned long long* bar = &sm.bar_depth[tile_seq & 1u];
-          mbar_expect_tx(bar, wb * nr);
-          for (uint32_t r = 0; r < nr; ++r)
-            bulk_g2s(&sm.depth[tile_seq & 1u][r][0], depth + (size_t) (r0 + r) * cam.cols + c0, wb, bar);
-        }
+      if (st.tile_a == kNoTicket) {
+        st.tile_a = st.tile_b, st.tile_b = kNoTicket, st.a_issued = false;
+        if (st.tile_a == kNoTicket)
+          st.tile_a = claim(q->q_tile, plan.shard);
+      }
+      if (st.tile_a < plan.n_tiles) {
+        if (!st.a_issued)
+          issue_depth(f, cam, depth, plan, sm, st, tile_seq, bulk_depth);
+        it.kind = kItemTile, it.arg = f.band_lo + st.tile_a;
+        it.pad[0] = st.a_c0, it.pad[1] = st.a_r0;
+        st.tile_a = kNoTicket, st.a_issued = false;
         return;
       }
       st.tile_open = false;
@@ -944,7 +1020,10 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
   uint32_t tile_seq = 0, planes_seq = 0, iter = 0;
   SchedState sched; // thread 0
   sched.chunk_open = true, sched.tile_open = true, sched.drained = false, sched.peeked = false;
-  sched.next_chunk = blockIdx.x, sched.next_tile = blockIdx.x, sched.ticket = kNoTicket;
+  sched.next_chunk = blockIdx.x, sched.tile_a = blockIdx.x, sched.tile_b = kNoTicket, sched.ticket = kNoTicket;
+  sched.a_issued = false, sched.a_c0 = 0, sched.a_r0 = 0;
+  if (tid == 0 && sched.tile_a < plan.n_tiles) // the first tile is assigned statically: its depth rows start moving now
+    issue_depth(f, cam, depth, plan, sm, sched, 0, bulk_depth);
 
   unsigned long long cta_updated = 0;
 #ifdef MRH_FUSED_DEBUG
@@ -996,7 +1075,7 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
     if (kind == kItemExit)
       break;
     if (tid == 0)
-      prefetch_claims(m, plan, sm, sched);
+      prefetch_claims(m, f, cam, depth, plan, sm, sched, tile_seq + (kind == kItemTile ? 1u : 0u), bulk_depth);
     if (kind == kItemChunk) {
       role_chunk<FUSE_GC>(m, f, cam, pose, it.arg, n_live, sm);
     } else if (kind == kItemTile) {

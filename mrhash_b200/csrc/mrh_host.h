@@ -118,8 +118,6 @@ struct mrh_map {
   bool use_fused = true, use_bulk_depth = true;
   int fused_grid = 0, fused_ctas_per_sm = 0;
   int fused_pref_num = 0, fused_pref_den = 4; // CTAs in slots < num of every den prefer fusion items over ray tiles
-  uint32_t* d_tile_order = nullptr; // ray tiles, image border first (rebuilt when the image size changes)
-  uint32_t tile_order_rows = 0, tile_order_cols = 0;
   uint32_t fuse_tag = 0;                      // tag of the last frame's fusion-queue entries (never reset)
   float shortcut_size = 0.f, shortcut_ext = 0.f; // parameters shortcut_radius was verified for
   int shortcut_radius = 0;

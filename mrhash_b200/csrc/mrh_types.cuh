@@ -164,7 +164,6 @@ struct MapDev {
   FuseEntry* fq;    // fusion queue of the fused frame kernel
   GcEntry* gc_list; // blocks to remove at the end of the frame
   FrameQueues* fqs; // queue words of the fused frame kernel
-  const uint32_t* tile_order; // ray tiles of the fused kernel, image border first
   VisEntry* realloc_list; // variance path: blocks queued for re-allocation at resolution 1, then the re-integration list
   unsigned long long* reint_keys; // variance path: keys of the blocks re-fused by k_reintegrate
   unsigned long long* zbuf;
