@@ -1,24 +1,31 @@
 #!/usr/bin/env python
 """bench.py — RGB-D frames/s (and Mvoxels-updated/s, % of HBM roofline) of the compute() hot path.
 
-Workload (BASELINE.json configs[1]): synthetic 640x480 orbiting-camera RGB-D stream (scene S2 of
-SURVEY.md §8d, replica.cfg parameters), one "step" = one frame through compute(): block
-allocation -> visibility -> TSDF fusion + garbage collection.
+Workload: synthetic orbiting-camera RGB-D stream (scene S2 of SURVEY.md §8d, replica.cfg parameters),
+640x480 / 1000 frames per orbit at N = 1 (BASELINE.json configs[1]), 1280x960 / 2000 frames per orbit
+at N > 1 (configs[3]) unless --width/--height say otherwise. One "step" = one frame through compute():
+block allocation -> visibility -> TSDF fusion + garbage collection (one persistent kernel, k_frame).
 
   value  : frames/s with the frames already resident in HBM (device pointers handed to the C ABI),
            L2 flushed before every step, per-step CUDA-event time summed, max over ranks.
-  e2e    : frames/s through the public GeoWrapper API with HOST buffers: per step setCurrPose +
-           setDepthImage + setRGBImage (pinned staging + H2D) + compute() + getStats() (D2H read).
-  roofline: the dominant kernel, algorithmic bytes / CUDA-event kernel time vs MEASURED_PEAKS.json.
+  e2e    : frames/s through the public GeoWrapper API with HOST buffers, pipelined the way a streaming
+           caller uses it: per step setCurrPose + setDepthImage + setRGBImage (H2D from page-locked
+           frames, mrh_set_ingest_mode 2) + compute() + the counters of the previous frame read back
+           (mrh_get_stats_pipelined); the transfer of frame k+1 overlaps the kernel of frame k.
+  roofline: k_frame, algorithmic bytes per frame / CUDA-event kernel time vs MEASURED_PEAKS.json.
   cpu_baseline: the CPU restatement (oracle/) with OpenMP on the host cores, bounded sample.
+  lidar, mesh_50M (N = 1): BASELINE configs[2] and configs[4] through the same public API (tools/bench_lidar.py,
+           tools/bench_mesh.py), each next to the reference kernels' time on the same input.
 
 `--impl reference` runs the UNMODIFIED reference kernels (oracle/_ref/libref_harness.so, compiled
 from /root/reference for sm_100a) on the same stream, host buffers in, the way GeoWrapper::compute
-drives them. N>1 (torchrun): the map is sharded by hash-bucket range, rank 0 ingests each frame and
-broadcasts it over NCCL; every rank allocates / fuses only the blocks it owns (starve frames
-min-reduce the z-buffer over the ranks). Two more keys at N>1: `replica_streams` (one unsharded
-stream per GPU, no collective) and `sharded_mesh` (boundary exchange + marching cubes in place +
-soup gather + weld, timed). stdout carries exactly one JSON line; everything else goes to stderr.
+drives them: `value` is the CUDA-event time of its integrate() section (device time, like ours),
+`e2e` its wall-clock frames/s with host buffers. N>1 (torchrun): the map is sharded by hash-bucket
+range, rank 0 ingests each frame and broadcasts it over NCCL; every rank allocates / fuses only the
+blocks it owns (starve frames min-reduce the z-buffer over the ranks). Two more keys at N>1:
+`replica_streams` (one unsharded stream per GPU, no collective) and `sharded_mesh` (boundary exchange
++ marching cubes in place + soup gather + weld, timed). stdout carries exactly one JSON line;
+everything else goes to stderr.
 """
 import argparse
 import json
@@ -36,7 +43,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
-COUNTERS_BYTES = 136  # sizeof(mrh::Counters), the read-back of getStats()
+COUNTERS_BYTES = 144  # the part of mrh::Counters that getStats() / mrh_get_stats_pipelined read back
 
 
 def parse():
@@ -45,12 +52,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=640)
-    ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--orbit-frames", type=int, default=1000, help="frames per full orbit of scene S2")
+    ap.add_argument("--width", type=int, default=0, help="default: 640 at --gpus 1, 1280 at --gpus > 1 (BASELINE configs[1] / configs[3])")
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--orbit-frames", type=int, default=0, help="frames per full orbit of scene S2 (default 1000 / 2000)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the lidar / mesh_50M keys (N = 1)")
+    args = ap.parse_args()
+    multi = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1
+    if not args.width:
+        args.width = 1280 if multi else 640
+    if not args.height:
+        args.height = args.width * 3 // 4
+    if not args.orbit_frames:
+        args.orbit_frames = 2000 if args.width >= 1280 else 1000
+    return args
+
+
+def workload(args):
+    """The same string in both arms (the driver compares config.workload)."""
+    return f"S2 orbiting-camera RGB-D stream {args.width}x{args.height} ({args.orbit_frames} frames/orbit), replica.cfg parameters (BASELINE configs[{3 if args.width >= 1280 else 1}])"
 
 
 class ClockSampler:
@@ -221,20 +242,23 @@ def run_reference(args, rank, world):
         os.chdir(cwd)
     finally:
         os.dup2(saved[0], 1), os.dup2(saved[1], 2)
-    fps = args.steps / dt
+    fps_wall = args.steps / dt
+    fps_dev = args.steps / (integ_ms * 1e-3) if integ_ms > 0 else None
     line = {
         **base,
-        "value": fps,
-        "ms_per_step": 1e3 * dt / args.steps,
+        "value": fps_dev if fps_dev else fps_wall,
+        "value_kind": "device time: CUDA events around VoxelContainer::integrate (voxel_data_structures.cpp:94-109), inputs already uploaded" if fps_dev else "wall clock",
+        "ms_per_step": (integ_ms / args.steps) if fps_dev else 1e3 * dt / args.steps,
         "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"S2 orbiting-camera RGB-D stream {args.width}x{args.height}, replica.cfg parameters", "num_sdf_blocks": NUM_SDF_BLOCKS, "hash_num_buckets": HASH_NUM_BUCKETS, "l2": "not flushed (host-driven, synchronous reference)"},
-        "integrate_only_fps": args.steps / (integ_ms * 1e-3) if integ_ms > 0 else None,
+        "config": {"workload": workload(args), "num_sdf_blocks": NUM_SDF_BLOCKS, "hash_num_buckets": HASH_NUM_BUCKETS, "l2": "not flushed (host-driven, synchronous reference)", "parallelism": "1 GPU (the reference has no multi-GPU path)"},
+        "integrate_only_fps": fps_dev,
+        "wall_clock_fps": fps_wall,
         "visible_blocks_last_frame": occupied,
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "kind": "reference", "cores": 1, "sample": f"{args.steps} frames; the reference has no CPU path: this is its own CUDA code (oracle/_ref, -arch=sm_100a) driven by one host thread"},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": fps_wall, "unit": "frames/s", "kind": "reference", "cores": 1, "sample": f"{args.steps} frames; the reference has no CPU path: this is its own CUDA code (oracle/_ref, -arch=sm_100a) driven by one host thread"},
+        "e2e": {"value": fps_wall, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "what": "wall clock, host buffers in, as GeoWrapper::compute drives the kernels"},
         "clocks": sampler.summary([(w0, w1)]),
         "gpu_launches": None,
     }
@@ -377,6 +401,13 @@ def main():
     ev_done.record(stream)
 
     host_us = {"setters": 0.0, "compute": 0.0, "read_result": 0.0}
+    if world == 1:
+        # streaming caller: page-locked frames are read by DMA while the previous frame's kernel runs
+        # (the frames of this pass are never modified), and every frame's counters reach the host one
+        # frame late instead of draining the device after each compute()
+        g.setIngestMode(2)
+        g.setStatsPipeline(True)
+    e2e_state = {"n": 0}
 
     def step_host(k):
         if world == 1:
@@ -388,7 +419,10 @@ def main():
             c1 = time.perf_counter()
             g.compute()
             c2 = time.perf_counter()
-            st = g.getStats()  # D2H read of the frame's counters (synchronises)
+            # D2H read of the step's result: the counters of the previous frame (its copy was enqueued
+            # behind that frame's kernel); the last frame's are read after the loop
+            st = g.getStatsPipelined(1) if e2e_state["n"] > 0 else None
+            e2e_state["n"] += 1
             c3 = time.perf_counter()
             host_us["setters"] += c1 - c0
             host_us["compute"] += c2 - c1
@@ -421,6 +455,9 @@ def main():
     t0 = time.perf_counter()
     for i in range(K):
         step_host(W + i)
+    if world == 1:
+        last_stats = g.getStatsPipelined(0)  # the result of the last step (waits for that frame only)
+        assert last_stats["frames"] >= K, last_stats
     e1.record(stream)
     g.synchronize()
     barrier()
@@ -439,17 +476,23 @@ def main():
         rgb_pg = [np.array(rgb_np[W + i]) for i in range(Kq)]
         g = new_map(args, rank, world, local)
         for k in range(W):
-            step_host(k)
+            g.setCurrPose(*poses[k])
+            g.setDepthImage(depth_np[k])
+            g.setRGBImage(rgb_np[k])
+            g.compute()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        g.setStatsPipeline(True)
         for i in range(Kq):
             g.setCurrPose(*poses[W + i])
             g.setDepthImage(depth_pg[i])
             g.setRGBImage(rgb_pg[i])
             g.compute()
-            g.getStats()
+            if i:
+                g.getStatsPipelined(1)
+        g.getStatsPipelined(0)
         dt = time.perf_counter() - t0
-        e2e_pageable = {"value": Kq / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / Kq, "steps": Kq, "what": "inputs in pageable host memory: staged through pinned buffers inside the setters"}
+        e2e_pageable = {"value": Kq / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / Kq, "steps": Kq, "what": "inputs in pageable host memory (what rgbd_runner.py hands over): copied into pinned staging inside the setters (default ingest mode), counters read one frame late"}
         g.close()
 
     # ---------------- N > 1 only: (i) one independent stream per GPU, (ii) sharded meshing ------------
@@ -507,18 +550,21 @@ def main():
     sampler.stop()
 
     peak, peak_src = peaks()
-    # slot 0 = k_front (ray walk + block insert, with the visibility pass of the live list running in
-    # the same launch), slot 2 = k_integrate (fusion + garbage collection); slot 1 is empty on the
-    # two-launch path
-    names = ["k_front", "k_integrate"]
-    per_kernel = {"k_front": {"ms_per_launch": kms[0] / max(kn[0], 1), "launches": kn[0]}, "k_integrate": {"ms_per_launch": kms[2] / max(kn[2], 1), "launches": kn[2]}}
-    # algorithmic bytes per launch: integrate = 24 B per updated voxel (12 read + 12
-    # written) + 32 B per visible block record + 7 B per pixel (depth + rgb read once)
-    bytes_integrate = (24.0 * stp["voxels_updated"] + 32.0 * stp["blocks_visible"]) / Kp + 7.0 * P
-    # front = depth read once + one 128 B bucket line per new block + 16 B per live entry read and
-    # rewritten + one 32 B record per visible block
-    bytes_front = 4.0 * P + 128.0 * stp["blocks_new"] / Kp + 32.0 * stp["live_blocks"] + 32.0 * stp["blocks_visible"] / Kp
-    algo = {"k_integrate": bytes_integrate, "k_front": bytes_front}
+    # profiling slot 0 = k_frame (the whole frame is one launch; on the every-n-th starve frame the GC
+    # tail kernels follow it and are not part of this window)
+    fused = os.environ.get("MRH_FRAME", "fused") != "split"  # the library's own switch (mrh_capi.cu)
+    # algorithmic bytes per frame: 7 B per pixel (depth + colour read once) + 24 B per
+    # visible / new block (its table entry) + 24 B per updated voxel (12 read + 12 written)
+    bytes_frame = 7.0 * P + (24.0 * (stp["blocks_visible"] + stp["blocks_new"]) + 24.0 * stp["voxels_updated"]) / Kp
+    if fused:
+        names = ["k_frame"]
+        per_kernel = {"k_frame": {"ms_per_launch": kms[0] / max(kn[0], 1), "launches": kn[0]}}
+        algo = {"k_frame": bytes_frame}
+    else:  # MRH_FRAME=split: the two-launch frame of round 1
+        names = ["k_front", "k_integrate"]
+        per_kernel = {"k_front": {"ms_per_launch": kms[0] / max(kn[0], 1), "launches": kn[0]}, "k_integrate": {"ms_per_launch": kms[2] / max(kn[2], 1), "launches": kn[2]}}
+        algo = {"k_integrate": (24.0 * stp["voxels_updated"] + 32.0 * stp["blocks_visible"]) / Kp + 7.0 * P,
+                "k_front": 4.0 * P + 128.0 * stp["blocks_new"] / Kp + 32.0 * stp["live_blocks"] + 32.0 * stp["blocks_visible"] / Kp}
     dom = max(names, key=lambda k: per_kernel[k]["ms_per_launch"])
     achieved = algo[dom] / (per_kernel[dom]["ms_per_launch"] * 1e-3) / 1e9 if per_kernel[dom]["ms_per_launch"] > 0 else 0.0
     traffic = None
@@ -528,6 +574,39 @@ def main():
             traffic = json.load(open(tpath)).get(dom)
         except Exception:
             traffic = None
+
+    # ---------------- N = 1: BASELINE configs[2] (LiDAR) and configs[4] (50 M-voxel mesh) ---------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        del depth, rgb, flush
+        torch.cuda.empty_cache()
+        try:
+            from oracle_lib import ref_available
+
+            with_ref = ref_available()
+        except Exception:
+            with_ref = False
+        log = lambda msg: print(msg, file=sys.stderr, flush=True)
+        try:
+            import bench_lidar
+
+            extras["lidar"] = bench_lidar.run(40, 5, with_ref)
+            for key in ("sdf_var_threshold=0.0", "sdf_var_threshold=0.005"):
+                row = extras["lidar"][key]
+                row["roofline"] = {"bound": "hbm", "achieved": row["algorithmic_bytes_per_frame"] / (row["device_ms_per_frame"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
+                row["roofline"]["frac"] = row["roofline"]["achieved"] / peak
+        except Exception as e:  # an extra must never take the headline line down with it
+            extras["lidar"] = {"error": repr(e)}
+        try:
+            import bench_mesh
+
+            extras["mesh_50M"] = bench_mesh.run(97657, 0.003, with_ref, log)
+            mrow = extras["mesh_50M"]
+            mrow["roofline"] = {"bound": "hbm", "kernel": "k_mc_blocks", "achieved": mrow["mc_kernel_gbs"], "peak": peak, "unit": "GB/s", "frac": mrow["mc_kernel_gbs"] / peak}
+        except Exception as e:
+            extras["mesh_50M"] = {"error": repr(e)}
 
     if rank == 0:
         cpu = None
@@ -548,7 +627,7 @@ def main():
             "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": f"S2 orbiting-camera RGB-D stream {args.width}x{args.height} ({args.orbit_frames} frames/orbit), replica.cfg parameters (BASELINE configs[1])",
+                "workload": workload(args),
                 "num_sdf_blocks": NUM_SDF_BLOCKS,
                 "hash_num_buckets": HASH_NUM_BUCKETS,
                 "l2": "flushed before every step (256 MiB memset, excluded from the per-step CUDA-event window)",
@@ -560,12 +639,13 @@ def main():
             "new_blocks_per_frame": b_new / K,
             "live_blocks_end": live,
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
-            "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()}},
+            "value_kind": "device time: CUDA events around each compute(), device-resident inputs, L2 flushed before every step",
+            "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()},
+                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back one frame late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame, counters read back every frame"},
             "gpu_launches": int(launches),
-            "roofline_integrate": {"bound": "hbm", "kernel": "k_integrate", "achieved": algo["k_integrate"] / (per_kernel["k_integrate"]["ms_per_launch"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": algo["k_integrate"] / (per_kernel["k_integrate"]["ms_per_launch"] * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": algo["k_integrate"]},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
             "kernels": per_kernel,
-            "frame_algorithmic_bytes": 7.0 * P + (24.0 * (b_vis + b_new) + 24.0 * v_upd) / K,
+            "frame_algorithmic_bytes": 7.0 * P * world + (24.0 * (b_vis + b_new) + 24.0 * v_upd) / K,
             "clocks": sampler.summary([tuple(w) for w in windows]),
         }
         if cpu is not None:
@@ -573,6 +653,7 @@ def main():
         if e2e_pageable is not None:
             line["e2e_pageable"] = e2e_pageable
         line.update(extra_multi)
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.cuda.synchronize()

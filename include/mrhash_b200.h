@@ -98,10 +98,17 @@ int mrh_get_pose_matrix(mrh_map* m, float out[16]);
 /* GeoWrapper::setCameraInLidar (geowrapper.cpp:94-96) */
 int mrh_set_camera_in_lidar(mrh_map* m, const float T[16]);
 
-/* Frame setters. Pageable host memory is copied before the call returns (the reference's setters
- * copy element-wise, geowrapper.cpp:261-273). Page-locked (cudaHostAlloc / cudaHostRegister) memory
- * is read by DMA without a staging copy, and that transfer completes inside the next mrh_compute():
- * such a buffer must not be modified between the setter and the return of mrh_compute(). */
+/* Frame setters. By default every host buffer is copied before the call returns (the reference's
+ * setters copy element-wise, geowrapper.cpp:261-273): the caller may reuse it at once.
+ * mrh_set_ingest_mode lets a caller that holds page-locked (cudaHostAlloc / cudaHostRegister) frames
+ * skip that copy; pageable buffers are always staged.
+ *   0  (default) staged copy in the setter;
+ *   1  page-locked memory is read by DMA, the transfer completes inside the next mrh_compute(): the
+ *      buffer must not change between the setter and the return of mrh_compute();
+ *   2  page-locked memory is read by DMA and mrh_compute() does not wait for it (the transfer of frame
+ *      k+1 then overlaps the kernels of frame k): a buffer must not change until the SECOND next call
+ *      of the same setter has returned, or until mrh_synchronize(). */
+int mrh_set_ingest_mode(mrh_map* m, int mode);
 /* GeoWrapper::setDepthImage (geowrapper.cpp:246-274): host float32 [rows, cols], copied */
 int mrh_set_depth(mrh_map* m, const float* depth, int rows, int cols);
 /* GeoWrapper::setRGBImage (geowrapper.cpp:276-298): host uint8 [rows, cols, 3], copied */
@@ -209,6 +216,13 @@ int mrh_get_field(mrh_map* m, const char* name, double* out);
 int mrh_set_field(mrh_map* m, const char* name, double value);
 
 int mrh_get_stats(mrh_map* m, mrh_stats* out);
+/* Statistics without a stall per frame: once enabled, every mrh_compute() is followed by an asynchronous
+ * copy of the counters into page-locked memory; mrh_get_stats_pipelined(which = 1) returns the state
+ * after the frame BEFORE the last compute() (already there: no wait), which = 0 the state after the
+ * last one (waits for that frame only). A caller that reads which = 1 after every compute() sees every
+ * frame's result, one frame late, and never drains the device. */
+int mrh_set_stats_pipeline(mrh_map* m, int enabled);
+int mrh_get_stats_pipelined(mrh_map* m, int which, mrh_stats* out);
 int mrh_reset_stats(mrh_map* m);
 /* device time of the last compute() in ms (CUDAProfiler::CUDAEvent window, voxel_data_structures.cpp:94-109); synchronises */
 int mrh_last_compute_ms(mrh_map* m, float* ms);

@@ -127,6 +127,9 @@ SIGNATURES = {
     "mrh_mesh_local": ([_vp, _P(C.c_size_t)], _i),
     "mrh_copy_triangles_device": ([_vp, _vp, C.c_size_t], _i),
     "mrh_weld_device_soup": ([_vp, _vp, C.c_size_t, C.c_char_p], _i),
+    "mrh_set_ingest_mode": ([_vp, _i], _i),
+    "mrh_set_stats_pipeline": ([_vp, _i], _i),
+    "mrh_get_stats_pipelined": ([_vp, _i, _P(Stats)], _i),
     "mrh_selftest_div": ([_i, _f, C.c_uint64, C.c_uint64, _P(C.c_uint64)], _i),
     "mrh_get_block_shortcut_radius": ([_vp, _P(_i)], _i),
 }

@@ -132,6 +132,10 @@ static void free_map(mrh_map* m) {
   cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
+  cudaFreeHost(m->h_ctr_ring);
+  for (int i = 0; i < 2; ++i)
+    if (m->ev_ctr[i])
+      cudaEventDestroy(m->ev_ctr[i]);
   cudaFreeHost(m->h_heap_probe);
   for (int i = 0; i < 2; ++i) {
     cudaFreeHost(m->h_bounce[i]);
@@ -218,7 +222,7 @@ static void staged_copy(void* dst, const void* src, size_t bytes) {
 
 template <typename T, typename F>
 static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n, F fill) {
-  if (in.pending_direct) { // set twice without a compute() in between
+  if (in.pending_direct && m->ingest_mode != 2) { // set twice without a compute() in between
     CK(cudaEventSynchronize(in.copied[in.which]));
     in.pending_direct = false;
   }
@@ -233,12 +237,16 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
   }
   CK(cudaStreamWaitEvent(m->copy_stream, in.consumed[w], 0));
   bool direct = false;
-  if (src_or_null) {
+  if (src_or_null && m->ingest_mode != 0) {
     cudaPointerAttributes attr;
     direct = cudaPointerGetAttributes(&attr, src_or_null) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
   }
   if (direct) {
+    // mode 2: this device image was filled two setter calls ago; that transfer read a caller buffer
+    // which the caller may reuse from now on (the contract of mrh_set_ingest_mode)
+    if (m->ingest_mode == 2)
+      CK(cudaEventSynchronize(in.copied[w]));
     CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, m->copy_stream));
     CK(cudaEventRecord(in.copied[w], m->copy_stream));
     in.pending_direct = true;
@@ -597,10 +605,17 @@ static int compute_frame(mrh_map* m) {
       CK(cudaEventRecord(in->consumed[in->which], m->stream));
   // transfers that read the caller's page-locked memory directly: the caller owns it again on return
   for (Ingest* in : used)
-    if (in && in->pending_direct) {
+    if (in && in->pending_direct && m->ingest_mode != 2) {
       CK(cudaEventSynchronize(in->copied[in->which]));
       in->pending_direct = false;
     }
+  if (m->stats_pipeline) {
+    m->ctr_slot ^= 1;
+    CK(cudaMemcpyAsync(m->h_ctr_ring + m->ctr_slot, m->dev.ctr, offsetof(Counters, dbg), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaEventRecord(m->ev_ctr[m->ctr_slot], m->stream));
+    m->ctr_frames[m->ctr_slot] = m->frames_total;
+    m->ctr_filled              = std::min(m->ctr_filled + 1, 2);
+  }
   return 0;
 }
 
@@ -755,16 +770,63 @@ int mrh_set_shard(mrh_map* m, int shard_rank, int shard_world) {
   return 0;
 }
 
+static int fill_stats(const mrh_map* m, const Counters& c, uint64_t frames, mrh_stats* out);
+
+int mrh_set_ingest_mode(mrh_map* m, int mode) {
+  GUARD(m);
+  if (mode < 0 || mode > 2)
+    return fail("mrh_set_ingest_mode: mode must be 0, 1 or 2");
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+    if (in->pending_direct) {
+      CK(cudaEventSynchronize(in->copied[in->which]));
+      in->pending_direct = false;
+    }
+  m->ingest_mode = mode;
+  return 0;
+}
+
+int mrh_set_stats_pipeline(mrh_map* m, int enabled) {
+  GUARD(m);
+  if (enabled && !m->h_ctr_ring) {
+    CK(cudaMallocHost(&m->h_ctr_ring, 2 * sizeof(Counters)));
+    for (int i = 0; i < 2; ++i)
+      CK(cudaEventCreateWithFlags(&m->ev_ctr[i], cudaEventDisableTiming));
+  }
+  m->stats_pipeline = enabled != 0;
+  m->ctr_filled     = 0;
+  return 0;
+}
+
+int mrh_get_stats_pipelined(mrh_map* m, int which, mrh_stats* out) {
+  GUARD(m);
+  if (!out)
+    return fail("null argument");
+  if (!m->stats_pipeline)
+    return fail("mrh_get_stats_pipelined: enable mrh_set_stats_pipeline first");
+  // which = 1: the frame before the last compute() (its copy has normally landed: no wait);
+  // which = 0: the last compute() (waits for that frame)
+  if (which != 0 && which != 1)
+    return fail("mrh_get_stats_pipelined: which must be 0 or 1");
+  if (m->ctr_filled < 1 + which)
+    return fail("mrh_get_stats_pipelined: no such frame yet");
+  const int slot = m->ctr_slot ^ which;
+  CK(cudaEventSynchronize(m->ev_ctr[slot]));
+  return fill_stats(m, m->h_ctr_ring[slot], m->ctr_frames[slot], out);
+}
+
 int mrh_get_stats(mrh_map* m, mrh_stats* out) {
   GUARD(m);
   if (!out)
     return fail("null argument");
-  CK(cudaMemcpyAsync(m->h_ctr, m->dev.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, m->stream));
+  CK(cudaMemcpyAsync(m->h_ctr, m->dev.ctr, offsetof(Counters, dbg), cudaMemcpyDeviceToHost, m->stream));
   CK(cudaStreamSynchronize(m->stream));
-  const Counters& c   = *m->h_ctr;
+  return fill_stats(m, *m->h_ctr, m->frames_total, out);
+}
+
+static int fill_stats(const mrh_map* m, const Counters& c, uint64_t frames, mrh_stats* out) {
   if (c.fault)
     return fail("frame kernel watchdog: a wait inside k_frame hit its iteration bound (internal error, results are invalid)");
-  out->frames         = m->frames_total;
+  out->frames         = frames;
   out->rays_valid     = c.rays_valid;
   out->blocks_new     = c.blocks_new;
   out->blocks_visible = c.blocks_visible;

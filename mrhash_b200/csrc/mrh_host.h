@@ -127,6 +127,18 @@ struct mrh_map {
   uint64_t launches     = 0;
   uint64_t h2d_bytes    = 0;
   mrh::Counters* h_ctr  = nullptr; // pinned read-back
+  // how page-locked caller memory is ingested (mrh_set_ingest_mode): 0 = staged like pageable memory
+  // (the setter copies, reference semantics), 1 = DMA from the caller's buffer, awaited at the end of
+  // compute(), 2 = DMA from the caller's buffer, never awaited by compute() (streaming callers)
+  int ingest_mode = 0;
+  // pipelined statistics (mrh_set_stats_pipeline): every compute() is followed by an asynchronous copy
+  // of the counters into one of two pinned slots; mrh_get_stats_pipelined returns the previous frame's
+  mrh::Counters* h_ctr_ring = nullptr; // 2 pinned slots
+  cudaEvent_t ev_ctr[2]{};
+  uint64_t ctr_frames[2]{};            // frames_total at the time of the copy
+  bool stats_pipeline = false;
+  int ctr_slot        = 0;             // slot of the most recent compute()
+  int ctr_filled      = 0;             // copies issued so far (0, 1, 2+)
 
   // optional per-kernel timing (bench.py roofline pass): events between the kernels of a frame
   bool profiling = false;

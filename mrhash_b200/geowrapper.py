@@ -363,6 +363,20 @@ class GeoWrapper:
     def resetStats(self):
         check(self._lib.mrh_reset_stats(self._h))
 
+    def setIngestMode(self, mode):
+        """0: setters copy (default, reference semantics); 1 / 2: page-locked inputs are read by DMA
+        (include/mrhash_b200.h, mrh_set_ingest_mode, for the lifetime contract of mode 2)."""
+        check(self._lib.mrh_set_ingest_mode(self._h, int(mode)))
+
+    def setStatsPipeline(self, enabled):
+        check(self._lib.mrh_set_stats_pipeline(self._h, 1 if enabled else 0))
+
+    def getStatsPipelined(self, which=1):
+        """Counters after the frame before the last compute() (which=1, no wait) or after the last one (which=0)."""
+        s = _capi.Stats()
+        check(self._lib.mrh_get_stats_pipelined(self._h, int(which), C.byref(s)))
+        return s.as_dict()
+
     def lastComputeMs(self):
         ms = C.c_float()
         check(self._lib.mrh_last_compute_ms(self._h, C.byref(ms)))
