@@ -180,10 +180,16 @@ static void refresh_map_params(mrh_map* m) {
   if (p.shard_world > 1) {
     d.shard_lo = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) p.shard_rank / (uint64_t) p.shard_world);
     d.shard_hi = (uint32_t) ((uint64_t) d.num_buckets * (uint64_t) (p.shard_rank + 1) / (uint64_t) p.shard_world);
-    d.shard_tag = (uint32_t) p.shard_rank << 28;
+    // starve z-buffer ids: the rank takes just the bits it needs, the voxel id the rest (k_starve raises
+    // the sticky fault word if a frame ever has more visible voxels than that field can name)
+    uint32_t rank_bits = 0;
+    while ((1u << rank_bits) < (uint32_t) p.shard_world)
+      ++rank_bits;
+    d.starve_id_bits = 32u - rank_bits;
+    d.shard_tag      = rank_bits ? (uint32_t) p.shard_rank << d.starve_id_bits : 0u;
   } else {
     d.shard_lo = 0, d.shard_hi = d.num_buckets;
-    d.shard_tag = 0;
+    d.shard_tag = 0, d.starve_id_bits = 32u;
   }
 }
 
@@ -824,6 +830,9 @@ int mrh_get_stats(mrh_map* m, mrh_stats* out) {
 }
 
 static int fill_stats(const mrh_map* m, const Counters& c, uint64_t frames, mrh_stats* out) {
+  if (c.fault == 2)
+    return fail("starve pass: more visible voxels than the z-buffer id field can name (%u bits with %d shards): weights were not decremented for the excess; use fewer shards or a smaller map per shard",
+                m->dev.starve_id_bits, m->p.shard_world);
   if (c.fault)
     return fail("frame kernel watchdog: a wait inside k_frame hit its iteration bound (internal error, results are invalid)");
   out->frames         = frames;

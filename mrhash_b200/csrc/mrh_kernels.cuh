@@ -399,6 +399,12 @@ __global__ void __launch_bounds__(128) k_starve(MapDev m, FrameDev f, CameraDev 
     const VisEntry e = m.vis[bi];
     if (e.val & 0x80000000u)
       continue;
+    if ((bi >> (m.starve_id_bits - 9u)) != 0u) {
+      // the id 512 * bi + i would run into the rank field: two voxels would share a z-buffer value
+      if (tid == 0)
+        *reinterpret_cast<volatile uint32_t*>(&m.ctr->fault) = 2u;
+      continue;
+    }
     uint8_t* base = m.pool + (size_t) e.val * kBlockBytes;
 #pragma unroll 1
     for (int j = 0; j < 4; ++j) {

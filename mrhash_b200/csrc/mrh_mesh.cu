@@ -247,8 +247,30 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
             st.recs.swap(keep.recs);
             st.voxels.swap(keep.voxels);
           }
-          if (insert_from_host(m, in_recs.data(), in_vox.data(), in_recs.size()))
-            return 1;
+          {
+            // Paging a region in must not lose blocks: refuse up front when the pool cannot take the
+            // region (the records go back to the host store untouched), and hand them back as well if
+            // the insert itself reports a shortfall.
+            auto give_back = [&]() {
+              st.recs.insert(st.recs.end(), in_recs.begin(), in_recs.end());
+              st.voxels.insert(st.voxels.end(), in_vox.begin(), in_vox.end());
+            };
+            mrh_stats s0;
+            if (mrh_get_stats(m, &s0)) {
+              give_back();
+              return 1;
+            }
+            if ((int64_t) in_recs.size() > s0.heap_free) {
+              give_back();
+              return fail("extractMesh: the region holds %zu blocks but the pool has %lld free: a map larger than num_sdf_blocks cannot be meshed in one region - "
+                          "raise num_sdf_blocks (currently %llu)",
+                          in_recs.size(), (long long) s0.heap_free, (unsigned long long) m->num_sdf_blocks);
+            }
+            if (insert_from_host(m, in_recs.data(), in_vox.data(), in_recs.size())) {
+              give_back();
+              return 1;
+            }
+          }
           if (run_marching_cubes(m, force_generic))
             return 1;
           if (mrh_stream_all_out(m))

@@ -351,9 +351,27 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   }
 
   // Streamer::streamInToGPU (streamer.cpp:358-378) for a selection of host-store records.
+  static int insert_from_host_unchecked(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n);
+
+  // k_insert_blocks skips a record whose block cannot be placed (pool or table full) and only counts
+  // it; a caller that then dropped the record from the host store would lose the block for good.
+  // The counters are compared around the insert and a shortfall is an error: the callers leave the
+  // host store untouched in that case.
   int insert_from_host(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
     if (n == 0)
       return 0;
+    mrh_stats s0, s1;
+    if (mrh_get_stats(m, &s0) || insert_from_host_unchecked(m, recs, voxels, n) || mrh_get_stats(m, &s1))
+      return 1;
+    const uint64_t lost = (s1.dropped_heap - s0.dropped_heap) + (s1.dropped_table - s0.dropped_table);
+    if (lost)
+      return fail("stream-in: %llu of %zu blocks did not fit on the device (free pool blocks before: %lld, table buckets: %llu); "
+                  "the host store keeps every record - enlarge num_sdf_blocks / hash_num_buckets or page with a smaller radius",
+                  (unsigned long long) lost, n, (long long) s0.heap_free, (unsigned long long) m->hash_num_buckets);
+    return 0;
+  }
+
+  static int insert_from_host_unchecked(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
     uint32_t n_low = 0;
     for (size_t i = 0; i < n; ++i)
       n_low += recs[i].resolution != 0;

@@ -149,7 +149,8 @@ struct MapDev {
   uint32_t num_buckets, capacity, num_blocks;
   uint32_t bucket_magic; // floor(2^32 / num_buckets): block_hash_fast needs no integer division
   uint32_t shard_lo, shard_hi; // owned range of reference hash buckets (multi-GPU partition)
-  uint32_t shard_tag;          // shard_rank << 28: makes the starve z-buffer ids unique across ranks
+  uint32_t shard_tag;          // shard_rank << starve_id_bits: makes the starve z-buffer ids unique across ranks
+  uint32_t starve_id_bits;     // low bits of a z-buffer id that name the voxel (512 * visible index + voxel); the rest is the rank
   int block_shortcut_radius;   // voxel_to_block_1(v) == v >> 3 verified for |v| <= radius (0: never take the shortcut)
   int fast_div;                // 1: voxel size, depth range and extents allow the shared-reciprocal divisions (mrh_div.cuh)
   unsigned long long* keys;

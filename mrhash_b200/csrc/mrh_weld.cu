@@ -44,11 +44,20 @@ namespace {
     return (uint32_t) (h >> 32);
   }
 
-  // key of soup vertex i (mesh_extractor.cpp:196-207 exact, :224-240 quantised)
+  // key of soup vertex i (mesh_extractor.cpp:196-207 exact, :224-240 quantised).
+  // Exact mode: the reference's map is unordered_map<Vector3d, int, Vector3dHash, Vector3dEqual>
+  // (mesh_extractor.cuh:25-36): the hash runs over the 24 BYTES of the vertex, equality is a == b.
+  // Two vertices therefore meet only if their bytes agree (-0.0 and +0.0 hash apart, so they stay two
+  // vertices unless their hashes happen to share a bucket), and a vertex with a NaN coordinate never
+  // equals anything, itself included: the key is the bit pattern, and a NaN vertex gets a key of its own
+  // (0xFFFFFFFF in x is a NaN pattern, so no non-NaN vertex can produce it).
   __device__ __forceinline__ Key3 vertex_key(const float* __restrict__ soup, uint32_t i, double inv_eps) {
     const float* v = soup + (size_t) i * 6;
-    if (inv_eps == 0.0)
+    if (inv_eps == 0.0) {
+      if (v[0] != v[0] || v[1] != v[1] || v[2] != v[2])
+        return {0xFFFFFFFFu, i, 0u};
       return {__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2])};
+    }
     return {(uint32_t) (int) floor((double) v[0] * inv_eps), (uint32_t) (int) floor((double) v[1] * inv_eps), (uint32_t) (int) floor((double) v[2] * inv_eps)};
   }
 

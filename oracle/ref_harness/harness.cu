@@ -21,32 +21,20 @@
 
 #include "camera.cuh"
 #include "marching_cubes.cuh"
+#include "streamer.cuh"
 #include "voxel_data_structures.cuh"
 
 using namespace cupanutils::cugeoutils;
 
-// The reference defines these members in mesh_extractor.cpp (host, needs real Eigen). The harness
-// never calls them, but the constructor / vtable reference them, so give the linker empty bodies.
-namespace cupanutils {
-  namespace cugeoutils {
-    template <typename T>
-    void MeshExtractor<T>::processTriangles() {
-    }
-    template <typename T>
-    void MeshExtractor<T>::processTrianglesThread() {
-    }
-    // mesh_extractor.cuh already holds `template class MeshExtractor<Voxel>;`, so force the
-    // two bodies above to be emitted by odr-using them.
-    void (MeshExtractor<Voxel>::*const harness_keep_a)() = &MeshExtractor<Voxel>::processTriangles;
-    void (MeshExtractor<Voxel>::*const harness_keep_b)() = &MeshExtractor<Voxel>::processTrianglesThread;
-  } // namespace cugeoutils
-} // namespace cupanutils
+// MeshExtractor's host members (processTriangles, combine, removeDuplicate*) come from the reference's own
+// mesh_extractor.cpp, compiled into this library by oracle/Makefile against the Eigen stand-in.
 
 namespace {
   struct Ref {
     std::unique_ptr<GeometricVoxelContainer> container;
     std::unique_ptr<Camera> camera;
     std::unique_ptr<GeometricMarchingCubes> mc;
+    std::unique_ptr<GeometricStreamer> streamer; // declared after the container: destroyed first
     CUDAMatrixf depth_img;
     CUDAMatrixuc3 rgb_img;
     CUDAVectorf3 point_cloud;
@@ -229,6 +217,128 @@ uint32_t ref_extract_triangles(void* h, float* out, uint32_t max_out) {
     const uint32_t m = n < max_out ? n : max_out;
     memcpy(out, r->mc->h_triangles_, (size_t) m * sizeof(Triangle));
   }
+  return n;
+}
+
+// MeshExtractor::processTriangles (mesh_extractor.cpp:9-76), the reference's own host code, over a
+// caller-supplied soup of 72-byte Triangle records: vertex weld (exact for eps == 0, floor(v / eps)
+// buckets otherwise), degenerate-face and duplicate-face removal. merge != 0 appends to the mesh of
+// the previous call first (merge_mesh_, the path GeoWrapper::extractMesh takes per region).
+// Returns 0 and the sizes; ref_get_processed copies V (f64 x 3), F (i32 x 3), C (f64 x 3).
+int ref_process_soup(void* h, const float* soup, uint32_t n_tri, float eps, int merge, uint32_t* n_vertices, uint32_t* n_faces) {
+  Ref* r = (Ref*) h;
+  if (!r->mc || n_tri > r->mc->max_num_triangles_mesh_)
+    return 1;
+  memcpy(r->mc->h_triangles_, soup, (size_t) n_tri * sizeof(Triangle));
+  r->mc->num_triangles_              = n_tri;
+  r->mc->vertices_merging_threshold_ = eps;
+  r->mc->merge_mesh_                 = merge != 0;
+  if (!merge) {
+    r->mc->vertices_ = Eigen::MatrixXd();
+    r->mc->faces_    = Eigen::MatrixXi();
+    r->mc->colors_   = Eigen::MatrixXd();
+  }
+  r->mc->processTriangles();
+  *n_vertices = (uint32_t) r->mc->getVertices().rows();
+  *n_faces    = (uint32_t) r->mc->getFaces().rows();
+  return 0;
+}
+void ref_get_processed(void* h, double* V, int32_t* F, double* C) {
+  Ref* r = (Ref*) h;
+  const Eigen::MatrixXd& v = r->mc->getVertices();
+  const Eigen::MatrixXi& f = r->mc->getFaces();
+  const Eigen::MatrixXd& c = r->mc->getColors();
+  for (int i = 0; i < v.rows(); ++i)
+    for (int j = 0; j < 3; ++j)
+      V[3 * i + j] = v(i, j), C[3 * i + j] = c(i, j);
+  for (int i = 0; i < f.rows(); ++i)
+    for (int j = 0; j < 3; ++j)
+      F[3 * i + j] = f(i, j);
+}
+// the three mesh utilities the reference's own tests exercise (tests/test_marching_cubes.cpp:12-271)
+// on caller-supplied matrices; outputs are sized by the caller (n_v / n_f are upper bounds in, sizes out)
+int ref_remove_duplicate_vertices(void* h, const double* V, uint32_t n_v, const int32_t* F, uint32_t n_f, double eps, double* V_out, uint32_t* n_v_out, int32_t* F_out, int32_t* map_out) {
+  Ref* r = (Ref*) h;
+  Eigen::MatrixXd v(n_v, 3), vo;
+  Eigen::MatrixXi f(n_f, 3), fo;
+  Eigen::VectorXi map;
+  for (uint32_t i = 0; i < n_v; ++i)
+    for (int j = 0; j < 3; ++j)
+      v(i, j) = V[3 * i + j];
+  for (uint32_t i = 0; i < n_f; ++i)
+    for (int j = 0; j < 3; ++j)
+      f(i, j) = F[3 * i + j];
+  r->mc->removeDuplicateVerticesTriangle(v, f, eps, vo, fo, map);
+  *n_v_out = (uint32_t) vo.rows();
+  for (int i = 0; i < vo.rows(); ++i)
+    for (int j = 0; j < 3; ++j)
+      V_out[3 * i + j] = vo(i, j);
+  for (int i = 0; i < fo.rows(); ++i)
+    for (int j = 0; j < 3; ++j)
+      F_out[3 * i + j] = fo(i, j);
+  for (int i = 0; i < map.size(); ++i)
+    map_out[i] = map(i);
+  return 0;
+}
+int ref_remove_duplicate_faces(void* h, const int32_t* F, uint32_t n_f, int32_t* F_out, uint32_t* n_f_out) {
+  Ref* r = (Ref*) h;
+  Eigen::MatrixXi f(n_f, 3), fo;
+  for (uint32_t i = 0; i < n_f; ++i)
+    for (int j = 0; j < 3; ++j)
+      f(i, j) = F[3 * i + j];
+  r->mc->removeDuplicateFacesTriangle(f, fo);
+  *n_f_out = (uint32_t) fo.rows();
+  for (int i = 0; i < fo.rows(); ++i)
+    for (int j = 0; j < 3; ++j)
+      F_out[3 * i + j] = fo(i, j);
+  return 0;
+}
+
+// ---- the reference's Streamer (streamer.cpp / streamer.cu, unmodified), driven as GeoWrapper does
+// (geowrapper.cpp:74-76 create, :137-138 stream before integrate, :153 / :560 streamAllOut, :564 serializeData)
+int ref_streamer_create(void* h, uint32_t max_blocks_per_pass) {
+  Ref* r = (Ref*) h;
+  r->streamer = std::make_unique<GeometricStreamer>(r->container.get(), false, "ref_memory_allocation.txt", "ref_streamer_profiler");
+  const Eigen::Vector3f ext(r->container->voxel_extents_.x, r->container->voxel_extents_.y, r->container->voxel_extents_.z);
+  r->streamer->create(ext, max_blocks_per_pass, 0);
+  return 0;
+}
+// Streamer::stream (streamer.cpp:337-355) when the free pool drops to the threshold, as compute() does
+// (geowrapper.cpp:137-138); force != 0 streams unconditionally (tests/test_streamer.cu:92). Returns 1 if it streamed.
+int ref_stream(void* h, const float pos[3], float radius, int force) {
+  Ref* r = (Ref*) h;
+  if (!r->streamer)
+    return -1;
+  if (!force && r->container->getHeapHighFreeCount() > stream_threshold * r->container->num_sdf_blocks_)
+    return 0;
+  r->streamer->stream(Eigen::Vector3f(pos[0], pos[1], pos[2]), radius);
+  return 1;
+}
+int ref_stream_all_out(void* h) {
+  Ref* r = (Ref*) h;
+  if (!r->streamer)
+    return -1;
+  r->streamer->streamAllOut();
+  return 0;
+}
+int ref_serialize_data(void* h, const char* hash_path, const char* voxel_path) {
+  Ref* r = (Ref*) h;
+  if (!r->streamer)
+    return -1;
+  r->streamer->serializeData(hash_path, voxel_path);
+  return 0;
+}
+// debugCheckForDuplicates (streamer.cpp:401-446): percentage of (device table + host grid) records whose key repeats
+double ref_duplicates_ratio(void* h) {
+  Ref* r = (Ref*) h;
+  return r->streamer ? r->streamer->debugCheckForDuplicates() : -1.0;
+}
+uint32_t ref_grid_blocks(void* h) {
+  Ref* r = (Ref*) h;
+  uint32_t n = 0;
+  if (r->streamer)
+    for (const auto& kv : r->streamer->getGrid())
+      n += kv.second->getNElements();
   return n;
 }
 

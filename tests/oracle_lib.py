@@ -183,6 +183,63 @@ class RefCuda:
     def occupied(self):
         return self.lib.ref_current_occupied_blocks(self.h)
 
+    # ---- the reference's host mesh post-processing (mesh_extractor.cpp, unmodified, in oracle/_ref) ----
+    def process_soup(self, soup, eps, merge=False):
+        """MeshExtractor::processTriangles over a [T, 3, 6] float32 soup -> (V f64 [n,3], F i32 [m,3], C f64 [n,3])."""
+        soup = np.ascontiguousarray(soup, np.float32)
+        nv, nf = C.c_uint32(), C.c_uint32()
+        self.lib.ref_process_soup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        rc = self.lib.ref_process_soup(self.h, soup.ctypes.data, len(soup), eps, 1 if merge else 0, C.byref(nv), C.byref(nf))
+        assert rc == 0, "ref_process_soup: soup larger than max_num_triangles"
+        V, F, Cc = np.zeros((nv.value, 3)), np.zeros((nf.value, 3), np.int32), np.zeros((nv.value, 3))
+        self.lib.ref_get_processed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.ref_get_processed(self.h, V.ctypes.data, F.ctypes.data, Cc.ctypes.data)
+        return V, F, Cc
+
+    def remove_duplicate_vertices(self, V, F, eps):
+        V, F = np.ascontiguousarray(V, np.float64).reshape(-1, 3), np.ascontiguousarray(F, np.int32).reshape(-1, 3)
+        Vo, Fo, mp = np.zeros_like(V), np.zeros_like(F), np.zeros(len(V), np.int32)
+        n = C.c_uint32()
+        self.lib.ref_remove_duplicate_vertices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p]
+        self.lib.ref_remove_duplicate_vertices(self.h, V.ctypes.data, len(V), F.ctypes.data, len(F), eps, Vo.ctypes.data, C.byref(n), Fo.ctypes.data, mp.ctypes.data)
+        return Vo[: n.value], Fo, mp
+
+    def remove_duplicate_faces(self, F):
+        F = np.ascontiguousarray(F, np.int32).reshape(-1, 3)
+        Fo = np.zeros_like(F)
+        n = C.c_uint32()
+        self.lib.ref_remove_duplicate_faces.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+        self.lib.ref_remove_duplicate_faces(self.h, F.ctypes.data, len(F), Fo.ctypes.data, C.byref(n))
+        return Fo[: n.value]
+
+    # ---- the reference's Streamer (streamer.cpp / streamer.cu, unmodified, in oracle/_ref) ----
+    def streamer_create(self, max_blocks_per_pass=100000):
+        self.lib.ref_streamer_create.argtypes = [C.c_void_p, C.c_uint32]
+        assert self.lib.ref_streamer_create(self.h, max_blocks_per_pass) == 0
+
+    def stream(self, position, radius, force=False):
+        pos = (C.c_float * 3)(*[float(x) for x in position])
+        self.lib.ref_stream.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_int]
+        return self.lib.ref_stream(self.h, pos, radius, 1 if force else 0)
+
+    def stream_all_out(self):
+        self.lib.ref_stream_all_out.argtypes = [C.c_void_p]
+        assert self.lib.ref_stream_all_out(self.h) == 0
+
+    def serialize_data(self, hash_path, voxel_path):
+        self.lib.ref_serialize_data.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        assert self.lib.ref_serialize_data(self.h, hash_path.encode(), voxel_path.encode()) == 0
+
+    def duplicates_ratio(self):
+        self.lib.ref_duplicates_ratio.argtypes = [C.c_void_p]
+        self.lib.ref_duplicates_ratio.restype = C.c_double
+        return self.lib.ref_duplicates_ratio(self.h)
+
+    def grid_blocks(self):
+        self.lib.ref_grid_blocks.argtypes = [C.c_void_p]
+        self.lib.ref_grid_blocks.restype = C.c_uint32
+        return self.lib.ref_grid_blocks(self.h)
+
     def dump(self):
         n = self.lib.ref_dump(self.h, None, None, 0)
         entries = np.zeros((n, 5), np.int32)

@@ -10,7 +10,7 @@ from compare import canonical_triangles, compare_dumps
 from oracle_lib import Oracle, RefCuda, ref_available
 from test_parity_rgbd import NUM_BLOCKS, NUM_BUCKETS, feed, make_all
 
-from mrhash_b200 import GeoWrapper, synth
+from mrhash_b200 import GeoWrapper, _capi, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -185,3 +185,160 @@ def test_device_weld_matches_first_seen_merge(eps):
     # welding twice gives the same mesh (the device weld is deterministic)
     g2v = g.getVertices()
     assert np.array_equal(g2v, gv)
+
+
+# ---------------------------------------------------------------------------------------------
+# a14 pinned against the reference's OWN host code: mesh_extractor.cpp is compiled, unmodified,
+# into oracle/_ref (oracle/Makefile) and driven through ref_process_soup.
+# ---------------------------------------------------------------------------------------------
+def _weld_ours(g, soup, eps):
+    """mrh_weld_device_soup over a soup uploaded to the device."""
+    import torch
+
+    g._set("VerticesMergingThreshold", eps)
+    d = torch.from_numpy(np.ascontiguousarray(soup, np.float32)).cuda()
+    _capi.check(_capi.lib().mrh_weld_device_soup(g._h, d.data_ptr(), len(soup), None))
+    return g.getVertices(), g.getFaces(), g.getColors()
+
+
+def _hand_soups():
+    """Soups that hit every branch of processTriangles, among them the hand meshes of the reference's
+    tests/test_marching_cubes.cpp:126-215 (REMOVE_DUPL_VERTICES basic_zero / basic_nonzero) as triangles."""
+    rng = np.random.default_rng(5)
+    out = {}
+    # tests/test_marching_cubes.cpp:126-139: vertices 0 and 3 coincide
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 0]], np.float32)
+    f = np.array([[0, 1, 2], [3, 1, 2]])
+    out["ref_basic_zero"] = np.concatenate([v[f], np.zeros((2, 3, 3), np.float32)], axis=2)
+    # :171-184: vertex 3 within epsilon of vertex 0
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.0005, 0.0005, 0.0005]], np.float32)
+    out["ref_basic_nonzero"] = np.concatenate([v[f], np.ones((2, 3, 3), np.float32)], axis=2)
+    # :91-101 duplicate faces, after welding
+    v = rng.random((6, 3)).astype(np.float32)
+    f = np.array([[0, 1, 2], [2, 3, 4], [0, 1, 2], [4, 5, 0], [2, 3, 4]])
+    out["duplicate_faces"] = np.concatenate([v[f], rng.random((5, 3, 3)).astype(np.float32)], axis=2)
+    # degenerate triangles (two corners weld together) and fully collapsed ones
+    v = rng.random((5, 3)).astype(np.float32)
+    f = np.array([[0, 0, 1], [1, 2, 3], [4, 4, 4], [3, 2, 1]])
+    out["degenerate"] = np.concatenate([v[f], rng.random((4, 3, 3)).astype(np.float32)], axis=2)
+    # signed zeros: vertices on the coordinate planes, reached as -0.0 and +0.0
+    z = np.array([[0.0, 0.5, 1.0], [-0.0, 0.5, 1.0], [1.0, -0.0, 0.0], [1.0, 0.0, -0.0], [2.0, 2.0, 2.0]], np.float32)
+    f = np.array([[0, 2, 4], [1, 3, 4], [0, 3, 4], [1, 2, 4]])
+    out["signed_zero"] = np.concatenate([z[f], rng.random((4, 3, 3)).astype(np.float32)], axis=2)
+    # a few thousand triangles on a coarse lattice: heavy welding, many repeated and degenerate faces
+    lattice = (rng.integers(-6, 7, (4000, 3, 3)) * np.float32(0.25)).astype(np.float32)
+    out["lattice"] = np.concatenate([lattice, rng.random((4000, 3, 3)).astype(np.float32)], axis=2)
+    return out
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("eps", [0.0, 0.004])
+def test_weld_matches_reference_process_triangles(eps):
+    params = dict(synth.REPLICA_PARAMS)
+    g = GeoWrapper(**params, num_sdf_blocks=2000, hash_num_buckets=1000, max_num_triangles=100000)
+    ref = RefCuda(params, 2000, 1000, max_num_triangles=100000)
+    for name, soup in _hand_soups().items():
+        if name == "signed_zero" and eps == 0.0:
+            continue  # own test below
+        gv, gf, gc = _weld_ours(g, soup, eps)
+        rv, rf, rc = ref.process_soup(soup, eps)
+        assert gv.shape == rv.shape and gf.shape == rf.shape, (name, gv.shape, rv.shape, gf.shape, rf.shape)
+        assert np.array_equal(gv, rv) and np.array_equal(gf, rf) and np.array_equal(gc, rc), name
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_weld_of_a_real_soup_matches_reference_process_triangles():
+    """The 7-frame room: ~75 k triangles through the reference's processTriangles and through the device weld."""
+    for eps in (0.0, 0.004):
+        params = dict(synth.REPLICA_PARAMS)
+        params["vertices_merging_threshold"] = eps
+        fx, fy, cx, cy = synth.intrinsics(640, 480)
+        g = GeoWrapper(**params, num_sdf_blocks=NUM_BLOCKS, hash_num_buckets=NUM_BUCKETS, max_num_triangles=MAX_TRIS)
+        g.setCamera(fx, fy, cx, cy, 480, 640, params["min_depth"], params["max_depth"], 0)
+        for k in range(7):
+            t, q, depth, rgb = synth.rgbd_frame(k, n_frames=2000)
+            feed(g, [], t, q, depth, rgb)
+        g.extractMesh(None)
+        tris = g.getTriangles()
+        ref = RefCuda(params, 2000, 1000, max_num_triangles=len(tris) + 16)
+        rv, rf, rc = ref.process_soup(tris, eps)
+        gv, gf, gc = g.getVertices(), g.getFaces(), g.getColors()
+        print(f"[weld vs reference host code, eps={eps}] {len(tris)} triangles -> {len(gv)} vertices / {len(gf)} faces")
+        assert np.array_equal(gv, rv) and np.array_equal(gf, rf) and np.array_equal(gc, rc)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_weld_signed_zero_and_nan_follow_the_reference_map():
+    """The reference keys its exact map on the BYTES of a vertex (Vector3dHash, mesh_extractor.cuh:25-30)
+    and compares with a == b (:32-36): -0.0 and +0.0 meet only if their hashes share a bucket, a NaN
+    vertex never equals anything. Ours: bit-pattern keys, NaN vertices each their own class. The vertex
+    COUNT is compared (the reference's can be lower by the signed-zero pairs that collide in a bucket)."""
+    params = dict(synth.REPLICA_PARAMS)
+    g = GeoWrapper(**params, num_sdf_blocks=2000, hash_num_buckets=1000, max_num_triangles=1000)
+    ref = RefCuda(params, 2000, 1000, max_num_triangles=1000)
+    soup = _hand_soups()["signed_zero"]
+    gv, gf, _ = _weld_ours(g, soup, 0.0)
+    rv, rf, _ = ref.process_soup(soup, 0.0)
+    assert len(gv) == 5  # bit patterns: (+0, .5, 1), (-0, .5, 1), (1, -0, 0), (1, 0, -0), (2, 2, 2)
+    assert len(rv) in (3, 4, 5), len(rv)  # 5 unless a +-0 pair lands in one bucket of libstdc++'s table
+    if len(rv) == 5:
+        assert np.array_equal(gv, rv) and np.array_equal(gf, rf)
+    nan = soup.copy()
+    nan[0, 0, 0] = np.nan
+    nan[1, 0, 0] = np.nan  # two vertices with identical NaN payloads
+    gv, gf, _ = _weld_ours(g, nan, 0.0)
+    rv, rf, _ = ref.process_soup(nan, 0.0)
+    assert len(gv) == len(rv) and np.array_equal(gf, rf)
+    assert np.array_equal(np.isnan(gv), np.isnan(rv))
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_reference_mesh_utilities_known_answers():
+    """The reference's own gtest cases (tests/test_marching_cubes.cpp:91-215), run against the reference's
+    own code in oracle/_ref: the harness and the Eigen stand-in it is compiled against behave."""
+    params = dict(synth.REPLICA_PARAMS)
+    ref = RefCuda(params, 2000, 1000, max_num_triangles=16)
+    faces = np.array([[0, 1, 2], [2, 3, 4], [0, 1, 2], [4, 5, 6], [2, 3, 4]], np.int32)
+    assert len(ref.remove_duplicate_faces(faces)) == len(faces) - 2  # :91-101
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 0]], np.float64)
+    f = np.array([[0, 1, 2], [3, 1, 2]], np.int32)
+    uv, uf, mp = ref.remove_duplicate_vertices(v, f, 0.0)  # :126-169
+    assert len(uv) == 3 and np.array_equal(uv, v[:3]) and list(mp) == [0, 1, 2, 0] and np.array_equal(uf, [[0, 1, 2], [0, 1, 2]])
+    v[3] = [0.0005, 0.0005, 0.0005]
+    uv, uf, mp = ref.remove_duplicate_vertices(v, f, 0.001)  # :171-214
+    assert len(uv) == 3 and list(mp) == [0, 1, 2, 0]
+
+
+# ---------------------------------------------------------------------------------------------
+# a15 pinned against the reference's OWN streamer: streamer.cpp / streamer.cu are compiled,
+# unmodified, into oracle/_ref and driven the way GeoWrapper drives them.
+# ---------------------------------------------------------------------------------------------
+def _ply_payload_sorted(path):
+    pts, props = _read_ply_points(path)
+    raw = np.frombuffer(pts.tobytes(), np.uint8).reshape(len(pts), -1)
+    order = np.lexsort(raw.T[::-1])
+    return props, raw[order]
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_serialize_data_matches_reference_streamer(tmp_path):
+    """streamAllOut + serializeData (streamer.cpp:104-160, 216-281): the voxel cloud and the per-block
+    cloud (mean colour, mean weight) written by the reference's Streamer and by mrhash_b200 hold the same
+    records, byte for byte, once both files are sorted (the reference walks an unordered_map of chunks)."""
+    ours, ref, params = build_state(6)
+    ref.streamer_create()
+    assert compare_dumps(ours.dumpState(), ref.dump())["ok"]
+    ours.streamAllOut()
+    ref.stream_all_out()
+    assert ref.grid_blocks() == ours.storeSize()
+    oh, ov = str(tmp_path / "o_hash.ply"), str(tmp_path / "o_voxel.ply")
+    rh, rv = str(tmp_path / "r_hash.ply"), str(tmp_path / "r_voxel.ply")
+    ours.serializeData(oh, ov)
+    ref.serialize_data(rh, rv)
+    for a, b, what in ((ov, rv, "voxel"), (oh, rh, "hash")):
+        pa, da = _ply_payload_sorted(a)
+        pb, db = _ply_payload_sorted(b)
+        assert pa == pb, (what, pa, pb)
+        assert da.shape == db.shape, (what, da.shape, db.shape)
+        assert np.array_equal(da, db), (what, int((da != db).any(axis=1).sum()))
+    print(f"[serializeData vs reference] {len(_read_ply_points(ov)[0])} voxel points, {len(_read_ply_points(oh)[0])} block points identical")

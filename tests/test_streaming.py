@@ -148,3 +148,53 @@ def test_serialize_grid_checkpoint_round_trip(tmp_path):
     feed(b, 6)
     rep = compare_dumps(b.dumpState(), c.dumpState())
     assert rep["ok"] and rep["sdf_bitexact"], rep
+
+
+def test_paging_next_to_the_reference_streamer():
+    """f-1 against the reference's OWN Streamer (streamer.cpp / streamer.cu compiled unmodified into
+    oracle/_ref): the same 72-frame orbit in the same undersized pool, the reference paged the way
+    GeoWrapper::compute pages it (geowrapper.cpp:137-138: stream(camera position, max depth) in front of
+    integrate() whenever the free pool is at or below stream_threshold).
+    What must agree: nothing is lost on either side - after streamAllOut both stores hold the key set of
+    the unpaged map. What differs by design, stated as numbers: the reference keeps a re-allocated key
+    twice (its own test bounds the ratio, tests/test_streamer.cu:40-117), mrhash_b200 fuses the copies
+    when they are paged in together."""
+    from oracle_lib import RefCuda, ref_available
+
+    if not ref_available():
+        pytest.skip("oracle/_ref not built")
+    whole = make(60000, 0.0)
+    for k in range(N_FRAMES):
+        feed(whole, k)
+    ew, _ = whole.dumpState()
+    total = len(ew)
+    pool = int(total * 0.55)
+    small = make(pool, 0.15)
+    p = dict(synth.REPLICA_PARAMS)
+    p["max_depth"] = 2.0
+    p["n_frames_invalidate_voxels"] = 0
+    ref = RefCuda(p, pool, max(1000, pool // 2))
+    fx, fy, cx, cy = synth.intrinsics(W, H)
+    ref.set_camera(fx, fy, cx, cy, H, W, p["min_depth"], p["max_depth"], 0)
+    ref.streamer_create(pool)
+    ref_events = 0
+    for k in range(N_FRAMES):
+        t = feed(small, k)
+        _, _, depth, rgb = synth.rgbd_frame(k, n_frames=N_FRAMES, width=W, height=H)
+        ref_events += ref.stream(t, p["max_depth"]) == 1
+        ref.compute_rgbd(small.getCurrPose(), depth, rgb)
+    ref_dup_pct = ref.duplicates_ratio()
+    small.streamAllOut()
+    ref.stream_all_out()
+    es, _ = small.storeDump()
+    ours_keys = {tuple(e[:3]) for e in es.tolist()}
+    whole_keys = {tuple(e[:3]) for e in ew.tolist()}
+    n_ref = ref.grid_blocks()
+    ours_dup = len(es) - len(ours_keys)
+    print(
+        f"[paging vs reference] map {total} blocks, pool {pool}: ours {int(small._get('StreamEvents'))} stream events, {len(es)} stored records "
+        f"({ours_dup} repeated keys = {100.0 * ours_dup / len(es):.2f} %); reference {ref_events} stream events, {n_ref} stored records "
+        f"({n_ref - total} above the unpaged map's {total} = {100.0 * (n_ref - total) / max(n_ref, 1):.2f} %, its own duplicate check said {ref_dup_pct:.2f} % before the final stream-out)"
+    )
+    assert ours_keys == whole_keys and small.getStats()["dropped_heap"] == 0
+    assert ref_events >= 1 and n_ref >= total  # the reference lost nothing either (it may hold keys twice)
