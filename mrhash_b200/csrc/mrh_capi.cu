@@ -119,7 +119,7 @@ static void free_map(mrh_map* m) {
   MapDev& d = m->dev;
   cudaFree(d.keys), cudaFree(d.vals), cudaFree(d.heap), cudaFree(d.heap_low), cudaFree(d.pool), cudaFree(d.carved), cudaFree(d.stats);
   cudaFree(d.live[0]), cudaFree(d.live[1]), cudaFree(d.vis), cudaFree(d.fq), cudaFree(d.gc_list), cudaFree(d.fqs), cudaFree(d.realloc_list), cudaFree(d.reint_keys), cudaFree(d.ctr), cudaFree(d.zbuf);
-  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points, &m->in_normals})
     for (int i = 0; i < 2; ++i) {
       cudaFree(in->d_buf[i]), cudaFreeHost(in->h_buf[i]);
       if (in->copied[i])
@@ -323,7 +323,7 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   CK(cudaEventCreate(&m->ev0));
   CK(cudaEventCreate(&m->ev1));
   CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points, &m->in_normals})
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&in->copied[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&in->consumed[i], cudaEventDisableTiming));
@@ -516,18 +516,29 @@ int mrh_set_rgb_device(mrh_map* m, const uint8_t* d_rgb, int rows, int cols) {
 
 int mrh_set_points(mrh_map* m, const float* points, size_t n, const float* normals) {
   GUARD(m);
-  (void) normals; // projective sdf ignores normals (voxel_data_structures.cu:1317-1319)
   if (!points && n)
     return fail("GeoWrapper::setPointCloud|input should be a 2D numpy array");
   if (n == 0) {
     m->n_points = 0;
     return 0;
   }
-  if (!m->p.projective_sdf)
-    return fail("mrh_set_points: only projective_sdf=True is implemented (every shipped runner uses it)");
+  // projective_sdf = false lays the rays along the point normals and measures the sdf along them
+  // (voxel_data_structures.cu:957-961, 1251-1254, 1317-1321): it needs them. The reference's kernels
+  // read the normal of point i at normals[3 i] (the first of three eigenvectors per point, the layout
+  // the MAD-tree path of setPointCloud writes, geowrapper.cpp:386-398); its setPointCloud(points,
+  // normals) overload stores ONE vector per point and so makes the kernels read the normal of point
+  // 3 i, past the array for i >= n / 3 (geowrapper.cpp:489-500). Here normal i belongs to point i.
+  if (!m->p.projective_sdf && !normals)
+    return fail("mrh_set_points: projective_sdf = false needs per-point normals (setPointCloud(points, normals))");
   if (ingest_upload<float>(m, m->in_points, points, n * 3, [&](float* dst) { staged_copy(dst, points, sizeof(float) * n * 3); }))
     return 1;
-  m->d_points = (float*) m->in_points.d_buf[m->in_points.which];
+  m->d_points  = (float*) m->in_points.d_buf[m->in_points.which];
+  m->d_normals = nullptr;
+  if (normals && !m->p.projective_sdf) { // (the projective path never reads them, :1317-1319)
+    if (ingest_upload<float>(m, m->in_normals, normals, n * 3, [&](float* dst) { staged_copy(dst, normals, sizeof(float) * n * 3); }))
+      return 1;
+    m->d_normals = (float*) m->in_normals.d_buf[m->in_normals.which];
+  }
   m->n_points = n;
   return 0;
 }
@@ -589,7 +600,7 @@ static int compute_frame(mrh_map* m) {
         return 1;
     }
   }
-  Ingest* used[3] = {rgbd ? &m->in_depth : nullptr, rgbd ? &m->in_rgb : nullptr, m->n_points ? &m->in_points : nullptr};
+  Ingest* used[4] = {rgbd ? &m->in_depth : nullptr, rgbd ? &m->in_rgb : nullptr, m->n_points ? &m->in_points : nullptr, m->n_points && m->d_normals ? &m->in_normals : nullptr};
   // the ray walk needs the depth image (or the points) only: the colour transfer overlaps it and is
   // waited for in front of the first fusion kernel (integrate_rgbd)
   m->rgb_ready = nullptr;
@@ -782,7 +793,7 @@ int mrh_set_ingest_mode(mrh_map* m, int mode) {
   GUARD(m);
   if (mode < 0 || mode > 2)
     return fail("mrh_set_ingest_mode: mode must be 0, 1 or 2");
-  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points})
+  for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points, &m->in_normals})
     if (in->pending_direct) {
       CK(cudaEventSynchronize(in->copied[in->which]));
       in->pending_direct = false;

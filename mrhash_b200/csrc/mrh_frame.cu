@@ -358,7 +358,7 @@ static int fuse_points_typed(FrameCtx& c, const FrameDev& f, int key_bits) {
   const K hole = (K) ~(K) 0; // what the memset leaves in an unused slot; its low key_bits sort after every address
   if (cudaMemsetAsync(keys[0], 0xFF, sizeof(K) * items, s) != cudaSuccess)
     return fail("point path: clearing the record slots failed");
-  k_points_emit<K><<<(int) ((n + 255) / 256), 256, 0, s>>>(d, f, m->d_points, n, keys[0], m->d_upd_vals[0], slots);
+  k_points_emit<K><<<(int) ((n + 255) / 256), 256, 0, s>>>(d, f, m->d_points, m->d_normals, n, keys[0], m->d_upd_vals[0], slots);
   CKL();
   size_t tmp = m->sort_tmp_bytes;
   if (cub::DeviceRadixSort::SortPairs(m->d_sort_tmp, tmp, keys[0], keys[1], m->d_upd_vals[0], m->d_upd_vals[1], (int) items, 0, key_bits, s) != cudaSuccess)
@@ -418,7 +418,7 @@ int integrate_points(mrh_map* m) {
   if (c.var && top_up_low_heap(c))
     return 1;
   const int grid_pts = (int) ((n + 255) / 256);
-  k_alloc_points<<<grid_pts, 256, 0, s>>>(d, f, k, m->d_points, n);
+  k_alloc_points<<<grid_pts, 256, 0, s>>>(d, f, k, m->d_points, m->d_normals, n);
   CKL();
   k_visible<<<c.grid_list, 256, 0, s>>>(d, f, k, 0);
   CKL();

@@ -99,13 +99,14 @@ struct mrh_map {
   // ingest: copies run on their own stream into double-buffered device images, so the transfer of
   // frame k+1 overlaps the kernels of frame k (mrh_capi.cu: struct use in ingest_upload)
   cudaStream_t copy_stream = nullptr;
-  mrh::Ingest in_depth, in_rgb, in_points;
+  mrh::Ingest in_depth, in_rgb, in_points, in_normals;
   const float* depth_ptr = nullptr;
   const uint8_t* rgb_ptr = nullptr;
   cudaEvent_t rgb_ready  = nullptr; // set by compute(): the colour image is only needed by the fusion kernels
   int depth_rows = 0, depth_cols = 0, rgb_rows = 0, rgb_cols = 0;
   size_t n_points = 0;
   float* d_points = nullptr;
+  float* d_normals = nullptr; // per-point normals of the current cloud (nullptr: none given)
 
   // sharded starve frames: the frame stops after the z-buffer pass (mrh_compute_begin) so that the
   // caller can min-reduce the z-buffer over the ranks, and resumes in mrh_compute_end

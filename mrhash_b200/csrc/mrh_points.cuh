@@ -19,8 +19,11 @@ namespace mrh {
 
 
 // ray end points of one point (shared by the allocation and integration walks)
-// for_alloc: allocBlocks3DKernel :939-961; else integrate3DKernel :1229-1250 (projective sdf)
-__device__ __forceinline__ bool point_ray(const MapDev& m, const PoseDev& pose, f3 pcam, bool for_alloc, float& range, float& trunc, f3& pw_min, f3& pw_max) {
+// for_alloc: allocBlocks3DKernel :939-961; else integrate3DKernel :1229-1254.
+// nrm: the point's normal (the reference reads its `normals` array at 3 * point_idx, :937 / :1227: the
+// first eigenvector of the point); only used when projective_sdf is off, where both kernels lay the
+// ray along the normal (:959-960, :1252-1253). norm_dir returns the normalised normal.
+__device__ __forceinline__ bool point_ray(const MapDev& m, const PoseDev& pose, f3 pcam, f3 nrm, bool for_alloc, float& range, float& trunc, f3& pw_min, f3& pw_max, f3& norm_dir) {
   range = norm3df(pcam.x, pcam.y, pcam.z);
   if (for_alloc) {
     if (range == 0.f)
@@ -35,7 +38,13 @@ __device__ __forceinline__ bool point_ray(const MapDev& m, const PoseDev& pose, 
   if (dmin >= dmax)
     return false;
   f3 a, b;
-  if (for_alloc) {
+  norm_dir = {0.f, 0.f, 0.f};
+  if (!m.projective) {
+    norm_dir       = normalize3(nrm);
+    const float ka = fsub(dmin, range), kb = fsub(dmax, range);
+    a = {ffma(norm_dir.x, ka, pcam.x), ffma(norm_dir.y, ka, pcam.y), ffma(norm_dir.z, ka, pcam.z)};
+    b = {ffma(norm_dir.x, kb, pcam.x), ffma(norm_dir.y, kb, pcam.y), ffma(norm_dir.z, kb, pcam.z)};
+  } else if (for_alloc) {
     const float ka = fsub(dmin, range), kb = fsub(dmax, range);
     a = {ffma(dir.x, ka, pcam.x), ffma(dir.y, ka, pcam.y), ffma(dir.z, ka, pcam.z)};
     b = {ffma(dir.x, kb, pcam.x), ffma(dir.y, kb, pcam.y), ffma(dir.z, kb, pcam.z)};
@@ -48,7 +57,13 @@ __device__ __forceinline__ bool point_ray(const MapDev& m, const PoseDev& pose, 
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ points, uint32_t n_points) {
+__device__ __forceinline__ f3 point_normal(const float* __restrict__ normals, uint32_t i) {
+  if (!normals)
+    return {0.f, 0.f, 0.f};
+  return {__ldg(normals + 3 * (size_t) i), __ldg(normals + 3 * (size_t) i + 1), __ldg(normals + 3 * (size_t) i + 2)};
+}
+
+__global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, CameraDev cam, const float* __restrict__ points, const float* __restrict__ normals, uint32_t n_points) {
   __shared__ PoseDev pose;
   if (threadIdx.x == 0) {
     load_pose(f, pose);
@@ -67,8 +82,8 @@ __global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, Came
   if (i < n_points) {
     const f3 p = {__ldg(points + 3 * (size_t) i), __ldg(points + 3 * (size_t) i + 1), __ldg(points + 3 * (size_t) i + 2)};
     float range, trunc;
-    f3 a, b;
-    if (point_ray(m, pose, p, true, range, trunc, a, b)) {
+    f3 a, b, nd;
+    if (point_ray(m, pose, p, point_normal(normals, i), true, range, trunc, a, b, nd)) {
       dda.init(a, b, m.voxel_size, m.ext, true);
       active = true;
     }
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(256) k_alloc_points(MapDev m, FrameDev f, Came
 // One thread per point: voxel-level DDA, one record per visited voxel of an allocated block.
 // K = uint32_t while the pool address (+ hole key) fits 32 bits, else unsigned long long.
 template <typename K>
-__global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const float* __restrict__ points, uint32_t n_points, K* __restrict__ keys, float* __restrict__ vals, uint32_t slots) {
+__global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const float* __restrict__ points, const float* __restrict__ normals, uint32_t n_points, K* __restrict__ keys, float* __restrict__ vals, uint32_t slots) {
   __shared__ PoseDev pose;
   if (threadIdx.x == 0)
     load_pose(f, pose);
@@ -89,8 +104,8 @@ __global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const
     return;
   const f3 p = {__ldg(points + 3 * (size_t) i), __ldg(points + 3 * (size_t) i + 1), __ldg(points + 3 * (size_t) i + 2)};
   float range, trunc;
-  f3 a, b;
-  if (!point_ray(m, pose, p, false, range, trunc, a, b))
+  f3 a, b, nd;
+  if (!point_ray(m, pose, p, point_normal(normals, i), false, range, trunc, a, b, nd))
     return;
   DDA dda;
   dda.init(a, b, m.voxel_size, m.ext, false);
@@ -115,7 +130,11 @@ __global__ void __launch_bounds__(256) k_points_emit(MapDev m, FrameDev f, const
       const float vs  = fmul(m.voxel_size, i2f(scale));
       const f3 vp     = {fmul(i2f(v.x / scale), vs), fmul(i2f(v.y / scale), vs), fmul(i2f(v.z / scale), vs)};
       const f3 vc     = se3_mul(pose.Ri, pose.ti, vp);
-      float sdf       = fsub(range, norm3df(vc.x, vc.y, vc.z));
+      float sdf;
+      if (m.projective)
+        sdf = fsub(range, norm3df(vc.x, vc.y, vc.z));
+      else // :1320: dot(voxel_pos_camera - pcam, norm_dir)
+        sdf = dot3({fsub(vc.x, p.x), fsub(vc.y, p.y), fsub(vc.z, p.z)}, nd);
       if (sdf <= -trunc)
         break;
       sdf = (sdf >= 0.f) ? fminf(trunc, sdf) : fmaxf(-trunc, sdf);

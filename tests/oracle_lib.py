@@ -92,10 +92,11 @@ class Oracle:
         rgb = np.ascontiguousarray(rgb, np.uint8)
         self.lib.orc_compute_rgbd(self.h, pose.ctypes.data, depth.ctypes.data, rgb.ctypes.data, depth.shape[0], depth.shape[1])
 
-    def compute_points(self, pose44, points):
+    def compute_points(self, pose44, points, normals=None):
         pose = np.ascontiguousarray(pose44, np.float32)
         pts = np.ascontiguousarray(points, np.float32)
-        self.lib.orc_compute_points(self.h, pose.ctypes.data, pts.ctypes.data, None, pts.shape[0])
+        nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        self.lib.orc_compute_points(self.h, pose.ctypes.data, pts.ctypes.data, None if nrm is None else nrm.ctypes.data, pts.shape[0])
 
     def stats(self):
         s = FrameStats()
@@ -166,10 +167,11 @@ class RefCuda:
         rgb = np.ascontiguousarray(rgb, np.uint8)
         self.lib.ref_compute_rgbd(self.h, pose.ctypes.data, depth.ctypes.data, rgb.ctypes.data, depth.shape[0], depth.shape[1])
 
-    def compute_points(self, pose44, points):
+    def compute_points(self, pose44, points, normals=None):
         pose = np.ascontiguousarray(pose44, np.float32)
         pts = np.ascontiguousarray(points, np.float32)
-        self.lib.ref_compute_points(self.h, pose.ctypes.data, pts.ctypes.data, None, pts.shape[0])
+        nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        self.lib.ref_compute_points(self.h, pose.ctypes.data, pts.ctypes.data, None if nrm is None else nrm.ctypes.data, pts.shape[0])
 
     def last_integrate_ms(self):
         return self.lib.ref_last_integrate_ms(self.h)

@@ -82,3 +82,42 @@ def test_lidar_is_deterministic():
         dumps.append(ours.dumpState())
     assert np.array_equal(dumps[0][0][:, :4], dumps[1][0][:, :4])
     assert dumps[0][1].tobytes() == dumps[1][1].tobytes()
+
+
+def test_lidar_non_projective_sdf_along_the_normals():
+    """projective_sdf = False (voxel_data_structures.cu:957-961, 1251-1254, 1317-1321): the rays of the
+    allocation and of the voxel walk run along the point normals and the sdf is the distance along them.
+    Normals here: the room's surface normals towards the sensor, slightly perturbed, unnormalised (the
+    kernels normalise). Ours vs the CPU oracle (points in index order) and vs the reference kernels on
+    the voxels that cannot race (hit by exactly one point of the frame)."""
+    params = dict(synth.VBR_PARAMS)
+    params["projective_sdf"] = False
+    params["n_frames_invalidate_voxels"] = 0
+    ours, orc, ref = make(params)
+    rng = np.random.default_rng(3)
+    for k in range(2):
+        T, pts = synth.lidar_frame(k, noise_sigma=0.01)
+        nrm = -pts / np.linalg.norm(pts, axis=1, keepdims=True)
+        nrm = (nrm + 0.2 * rng.standard_normal(nrm.shape)).astype(np.float32) * np.float32(1.7)
+        ours.setCurrPoseMatrix(T)
+        ours.setPointCloud(pts, nrm)
+        ours.compute()
+        orc.compute_points(T, pts, nrm)
+        if ref is not None and k == 0:
+            ref.compute_points(T, pts, nrm)
+            (ea, va), (eb, vb) = ours.dumpState(), ref.dump()
+            assert np.array_equal(ea[:, :4], eb[:, :4])
+            once = va["weight"] == 1
+            assert once.sum() > 50000 and (vb["weight"][once] == 1).all()
+            assert np.array_equal(va["sdf"][once].view(np.uint32), vb["sdf"][once].view(np.uint32))
+            print(f"[lidar, sdf along normals, frame 0 vs reference] {int(once.sum())} single-hit voxels identical, {len(ea)} blocks")
+    st = ours.getStats()
+    assert st["dropped_heap"] == 0 and st["dropped_table"] == 0 and st["dropped_updates"] == 0
+    rep = compare_dumps(ours.dumpState(), orc.dump())
+    print("[lidar, sdf along normals, ours-vs-oracle] " + ", ".join(f"{k}={v}" for k, v in rep.items()))
+    budget = max(1, int(rep["voxels_compared"] * 1e-5))
+    assert rep["only_a"] == 0 and rep["only_b"] == 0 and rep["n_a"] > 1000
+    assert rep["weight_mismatch"] <= budget and rep["sdf_mismatch"] <= budget and rep["sum_squared_mismatch"] <= budget
+    # without normals the non-projective path refuses to run
+    with pytest.raises(RuntimeError, match="needs per-point normals"):
+        ours.setPointCloud(pts, False)

@@ -35,6 +35,8 @@ def feed(ours, others, t, q, depth, rgb):
     ours.setDepthImage(depth)
     ours.setRGBImage(rgb)
     ours.compute()
+    st = ours.getStats()  # a dropped block would be silent (the reference prints and goes on): every parity frame asserts none
+    assert st["dropped_heap"] == 0 and st["dropped_table"] == 0, st
     T = ours.getCurrPose()
     assert np.array_equal(T, synth.quat_to_matrix_f32(t, q))
     for o in others:
