@@ -85,10 +85,6 @@ struct HashSampler {
   __device__ __forceinline__ VoxVal voxel_point(f3 p, int* res) const {
     return voxel_at(world_to_voxel(p, m.voxel_size), res);
   }
-  // fetch at a point the caller knows to sit on the voxel lattice (this sampler converts the point anyway)
-  __device__ __forceinline__ VoxVal voxel_lattice(f3 p, i3, int* res) const {
-    return voxel_point(p, res);
-  }
 };
 
 // ---- shared-memory sampler: 10^3 halo around one resolution-0 block whose 27-neighbourhood holds
@@ -98,15 +94,6 @@ struct HaloSampler {
   const float* s_sdf;   // [1000]
   const uint32_t* s_cw; // [1000]
   i3 origin;            // voxel coordinate of halo cell (0,0,0) = 8 * block - 1
-  // The 8 fetches of a trilinear interpolation sit ON the voxel lattice (cell corner -+ half a voxel =
-  // a voxel centre, up to a few ulp): worldPointToVirtualVoxelPos (voxel_hash_utils.cuh:143-151) rounds
-  // to the nearest voxel, so the three divisions per fetch can only return the lattice index the
-  // caller already knows, as long as the float error stays far below half a voxel. With |voxel
-  // coordinate| < 2^18 the accumulated error of p / size is below 2^18 * 4 ulp = 0.125 voxel (checked
-  // per block, lattice_ok); the fetch then costs no arithmetic at all. 64 of the 72 fetches of a cell
-  // are of this kind; the 8 nearest-voxel fetches at the cell corners themselves are half-way between
-  // two voxels and keep the reference's arithmetic.
-  bool lattice_ok;
   __device__ __forceinline__ float voxel_size_point(f3) const {
     return m.voxel_size;
   }
@@ -121,16 +108,11 @@ struct HaloSampler {
   __device__ __forceinline__ VoxVal voxel_point(f3 p, int* res) const {
     return voxel_at(world_to_voxel(p, m.voxel_size), res);
   }
-  __device__ __forceinline__ VoxVal voxel_lattice(f3 p, i3 idx, int* res) const {
-    return lattice_ok ? voxel_at(idx, res) : voxel_point(p, res);
-  }
 };
 
 // trilinearInterpolation (voxel_data_structures.cu:260-338)
-// dual_idx: voxel index of the interpolation cell's lower corner `pos - half` when the caller knows it
-// (the halo path: pos is a cell corner of a resolution-0 voxel), passed on to voxel_lattice
 template <class S>
-__device__ __forceinline__ bool trilinear(const S& s, f3 pos, i3 dual_idx, float& dist) {
+__device__ __forceinline__ bool trilinear(const S& s, f3 pos, float& dist) {
   const float vs   = s.voxel_size_point(pos);
   const float half = fmul(vs, 0.5f);
   const f3 dual    = {fsub(pos.x, half), fsub(pos.y, half), fsub(pos.z, half)};
@@ -144,7 +126,7 @@ __device__ __forceinline__ bool trilinear(const S& s, f3 pos, i3 dual_idx, float
     const int dx = i & 1, dy = (i >> 1) & 1, dz = (i >> 2) & 1;
     const f3 vp  = {ffma(i2f(dx), vs, dual.x), ffma(i2f(dy), vs, dual.y), ffma(i2f(dz), vs, dual.z)};
     int res      = 0;
-    const VoxVal v = s.voxel_lattice(vp, {dual_idx.x + dx, dual_idx.y + dy, dual_idx.z + dz}, &res);
+    const VoxVal v = s.voxel_point(vp, &res);
     if (!(v.cw >> 24))
       return false;
     if (res > base_r) {
@@ -216,9 +198,8 @@ struct CellResult {
 
 // extractIsoSurfaceAtPosition up to the table lookup (marching_cubes.cu:72-214). Corner order of
 // p/d/cw: bit0 = +x, bit1 = +y, bit2 = +z (the reference's 000,001,010,011,100,101,110,111).
-// pi: voxel index of the cell's centre voxel (pf = pi * voxel size)
 template <class S, bool CHECK_NEIGHBOUR_SIZES>
-__device__ __forceinline__ void mc_cell(const S& s, const MapDev& m, f3 pf, i3 pi, CellResult& out) {
+__device__ __forceinline__ void mc_cell(const S& s, const MapDev& m, f3 pf, CellResult& out) {
   out.n_tri       = 0;
   const float vvs = s.voxel_size_point(pf);
   const float P   = fmul(vvs, 0.5f);
@@ -244,10 +225,7 @@ __device__ __forceinline__ void mc_cell(const S& s, const MapDev& m, f3 pf, i3 p
   for (int k = 0; k < 8; ++k) {
     const f3 p = {fadd(pf.x, (k & 1) ? sp[0] : sm[0]), fadd(pf.y, (k & 2) ? sp[1] : sm[1]), fadd(pf.z, (k & 4) ? sp[2] : sm[2])};
     float dist;
-    // corner = centre -+ half a voxel, interpolation cell = corner - half a voxel .. + half a voxel:
-    // its lower voxel is the centre voxel for a + corner, the one before it for a - corner
-    const i3 dual_idx = {pi.x - ((k & 1) ? 0 : 1), pi.y - ((k & 2) ? 0 : 1), pi.z - ((k & 4) ? 0 : 1)};
-    const bool valid  = trilinear(s, p, dual_idx, dist);
+    const bool valid = trilinear(s, p, dist);
     const VoxVal v   = s.voxel_point(p, nullptr);
     if (!valid) {
       if ((int) (v.cw >> 24) < m.min_weight_threshold)
@@ -373,11 +351,10 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
         const f3 pf  = {fmul(i2f(pi.x), m.voxel_size), fmul(i2f(pi.y), m.voxel_size), fmul(i2f(pi.z), m.voxel_size)};
         if (generic) {
           const HashSampler s{m};
-          mc_cell<HashSampler, true>(s, m, pf, pi, cell);
+          mc_cell<HashSampler, true>(s, m, pf, cell);
         } else {
-          const bool lattice_ok = max(max(abs(b.x), abs(b.y)), abs(b.z)) < (1 << 15) - 2; // |voxel coordinate| < 2^18
-          const HaloSampler s{m, s_sdf, s_cw, {b.x * 8 - 1, b.y * 8 - 1, b.z * 8 - 1}, lattice_ok};
-          mc_cell<HaloSampler, false>(s, m, pf, pi, cell);
+          const HaloSampler s{m, s_sdf, s_cw, {b.x * 8 - 1, b.y * 8 - 1, b.z * 8 - 1}};
+          mc_cell<HaloSampler, false>(s, m, pf, cell);
         }
       }
       // CTA-wide exclusive prefix sum of the triangle counts, one atomicAdd for the whole pass
