@@ -393,12 +393,18 @@ def main():
     depth_np, rgb_np = depth_h.numpy(), rgb_h.numpy()
     g = new_map(args, rank, world, local, max_num_triangles=4_000_000 if world > 1 else 1)
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
-    # N > 1: depth and colour travel in ONE buffer, one NCCL broadcast per frame
-    bcast = torch.empty(7 * P, dtype=torch.uint8, device=dev) if world > 1 else None
-    bcast_d = bcast[: 4 * P].view(torch.float32).view(args.height, args.width) if world > 1 else None
-    bcast_c = bcast[4 * P :].view(args.height, args.width, 3) if world > 1 else None
-    ev_ready, ev_done = torch.cuda.Event(), torch.cuda.Event()
-    ev_done.record(stream)
+    # N > 1: depth and colour travel in ONE buffer, one NCCL broadcast per frame; two buffers, so that
+    # the ingest + broadcast of frame k+1 (torch's stream) overlaps the kernels of frame k (the handle's
+    # stream). Ordering is by events only; the host never waits inside the loop.
+    bcast = [torch.empty(7 * P, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    bcast_d = [b[: 4 * P].view(torch.float32).view(args.height, args.width) for b in bcast] if world > 1 else None
+    bcast_c = [b[4 * P :].view(args.height, args.width, 3) for b in bcast] if world > 1 else None
+    ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in ev_done:
+        e.record(stream)
+    if world > 1:
+        g.setStatsPipeline(True)
 
     host_us = {"setters": 0.0, "compute": 0.0, "read_result": 0.0}
     if world == 1:
@@ -430,20 +436,23 @@ def main():
             return st
         # N > 1: rank 0 ingests the frame from its host buffers; the others receive it over NVLink.
         # The copy + broadcast run on torch's stream; the handle's stream is ordered after them
-        # (and the next broadcast after this frame's kernels) with events only.
+        # (and the broadcast that reuses this buffer, two frames on, after this frame's kernels).
+        b = e2e_state["n"] & 1
         g.setCurrPose(*poses[k])
-        torch.cuda.current_stream().wait_event(ev_done)
+        torch.cuda.current_stream().wait_event(ev_done[b])
         if rank == 0:
-            bcast_d.copy_(depth_h[k], non_blocking=True)
-            bcast_c.copy_(rgb_h[k], non_blocking=True)
-        dist.broadcast(bcast, 0)
-        ev_ready.record()
-        stream.wait_event(ev_ready)
-        g.setDepthImageDevice(bcast_d.data_ptr(), args.height, args.width)
-        g.setRGBImageDevice(bcast_c.data_ptr(), args.height, args.width)
+            bcast_d[b].copy_(depth_h[k], non_blocking=True)
+            bcast_c[b].copy_(rgb_h[k], non_blocking=True)
+        dist.broadcast(bcast[b], 0)
+        ev_ready[b].record()
+        stream.wait_event(ev_ready[b])
+        g.setDepthImageDevice(bcast_d[b].data_ptr(), args.height, args.width)
+        g.setRGBImageDevice(bcast_c[b].data_ptr(), args.height, args.width)
         run_frame(g)
-        ev_done.record(stream)
-        return g.getStats()
+        ev_done[b].record(stream)
+        st = g.getStatsPipelined(1) if e2e_state["n"] > 0 else None  # the previous frame's counters: no drain
+        e2e_state["n"] += 1
+        return st
 
     for k in range(W):
         step_host(k)
@@ -455,9 +464,8 @@ def main():
     t0 = time.perf_counter()
     for i in range(K):
         step_host(W + i)
-    if world == 1:
-        last_stats = g.getStatsPipelined(0)  # the result of the last step (waits for that frame only)
-        assert last_stats["frames"] >= K, last_stats
+    last_stats = g.getStatsPipelined(0)  # the result of the last step (waits for that frame only)
+    assert last_stats["frames"] >= K, last_stats
     e1.record(stream)
     g.synchronize()
     barrier()
@@ -641,7 +649,7 @@ def main():
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
             "value_kind": "device time: CUDA events around each compute(), device-resident inputs, L2 flushed before every step",
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()},
-                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back one frame late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame, counters read back every frame"},
+                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back one frame late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers (overlaps the previous frame's kernels), counters of every frame read back one frame late"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
             "kernels": per_kernel,
