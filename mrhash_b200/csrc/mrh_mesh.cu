@@ -157,7 +157,13 @@ namespace {
     const double t0 = now_ms();
     CK(cudaMemsetAsync(m->d_tri_count, 0, sizeof(uint32_t), m->stream));
     const uint32_t cap = (uint32_t) std::min<uint64_t>(m->max_num_triangles, 0xFFFFFFFFull);
-    k_mc_blocks<<<m->num_sms * 4, 256, 0, m->stream>>>(m->dev, m->live_cur, m->d_tri, m->d_tri_count, cap, force_generic, max_centers);
+    static int ctas_per_sm = 0; // resident CTAs per SM: the grid is exactly one wave of persistent CTAs
+    if (!ctas_per_sm) {
+      cudaFuncSetAttribute(k_mc_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_mc_blocks, kMcThreads, 0) != cudaSuccess || ctas_per_sm < 1)
+        ctas_per_sm = 4;
+    }
+    k_mc_blocks<<<m->num_sms * ctas_per_sm, kMcThreads, 0, m->stream>>>(m->dev, m->live_cur, m->d_tri, m->d_tri_count, cap, force_generic, max_centers);
     m->launches++;
     CK(cudaGetLastError());
     uint32_t n = 0;
@@ -191,8 +197,29 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
   if (!m)
     return fail("null handle");
   CK(cudaSetDevice(m->device));
-  if (mrh_stream_all_out(m))
+  // streamAllOut (geowrapper.cpp:153), in two halves: the copy to the host store now, the release of
+  // the device copy once it is known whether the map can be meshed where it already is (below)
+  HostStore& st           = m->store;
+  const size_t store_was  = st.recs.size();
+  const double t_begin    = now_ms();
+  const uint32_t frame    = m->frame_index;
+  bool device_copy_intact = false;
+  if (m->max_num_triangles != 0 && !getenv("MRH_MESH_ROUND_TRIP")) {
+    if (gather_to_host(m, st.recs, st.voxels))
+      return 1;
+    device_copy_intact = store_was == 0 && !st.recs.empty();
+  } else if (mrh_stream_all_out(m)) {
     return 1;
+  }
+  auto release_device_copy = [&]() -> int {
+    if (!device_copy_intact)
+      return 0;
+    device_copy_intact = false;
+    if (reset_map(m))
+      return 1;
+    m->frame_index = frame; // num_integrated_frames_ survives streaming
+    return cudaStreamSynchronize(m->stream) == cudaSuccess ? 0 : fail("extractMesh: release of the device copy failed");
+  };
   if (m->max_num_triangles == 0) {
     std::cerr << "GeoWrapper::extractMesh | no triangles to extract" << std::endl;
     return 0;
@@ -200,9 +227,7 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
   m->mesh.clear();
   m->soup_in_tri = m->soup_acc_n = 0;
   m->mesh_ms_stream = m->mesh_ms_kernel = m->mesh_ms_merge = m->mesh_ms_ply = 0;
-  const double t_begin = now_ms();
   std::cout << "GeoWrapper::extractMesh | extracting..." << std::endl;
-  HostStore& st     = m->store;
   const float size  = m->p.virtual_voxel_size;
   const float ext   = (float) m->p.voxel_extents_scale;
   const float radius = 10.f * m->cam.max_depth; // radius_scale_chunk (params.h:35)
@@ -232,6 +257,19 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
           for (size_t i = 0; i < st.recs.size(); ++i) {
             inside[i] = record_in_sphere(m, st.recs[i], centre, radius);
             n_in += inside[i];
+          }
+          if (device_copy_intact) {
+            // First region of a map that was entirely resident. If the region takes in every block and
+            // no second region follows, streaming the blocks back in would rebuild exactly the table the
+            // device still holds: mesh in place, then release (the second streamAllOut of the loop).
+            const bool single = n_in == st.recs.size() && x + radiusi >= hi[0] && y + radiusi >= hi[1] && z + radiusi >= hi[2];
+            if (single) {
+              if (run_marching_cubes(m, force_generic) || release_device_copy())
+                return 1;
+              continue;
+            }
+            if (release_device_copy())
+              return 1;
           }
           if (n_in == st.recs.size()) {
             in_recs.swap(st.recs); // the usual case: one region covers the whole map
@@ -277,6 +315,8 @@ int mrh_extract_mesh_ex(mrh_map* m, const char* path, int force_generic) {
             return 1;
         }
   }
+  if (release_device_copy()) // (empty store bounds: no region was visited)
+    return 1;
   {
     // processTriangles with merge_mesh_ = true over the soups of all regions, in region order
     const double t_weld = now_ms();

@@ -283,17 +283,67 @@ __device__ __forceinline__ void mc_emit(const CellResult& c, float* tri_out /* n
   }
 }
 
-// One CTA (256 threads, 2 voxels each) per live block.
+// Exact pre-filter of the halo path. Every value extractIsoSurfaceAtPosition can read for voxel
+// (x, y, z) of a resolution-0 block with resolution-0 neighbours lies in the voxel's 3 x 3 x 3
+// neighbourhood: the eight corners sit half a voxel away, and each corner's trilinear sample reads the
+// eight voxels around it with weights in [0, 1] (coordinates below 2^19 voxels keep positions exact to
+// vs / 16). A corner value is therefore either a convex combination of eight OBSERVED (weight > 0)
+// neighbourhood sdf values - evaluated with at most ~3e-5 * max|sdf| of rounding error - or, for a
+// corner with an unobserved voxel among its eight, the value of the voxel under the corner, which
+// must itself carry weight >= min_weight_threshold > 0 or the cell is abandoned. Hence, over the
+// observed voxels of the neighbourhood:
+//  * all sdf values > 1e-4 * max|sdf|  -> every corner is positive, cube index 0, no triangle;
+//  * all sdf values < -1e-4 * max|sdf| -> every corner is negative, cube index 255, no triangle;
+//  * no observed voxel at all -> the first corner falls back to an unobserved voxel and the cell is
+//    abandoned.
+// In each case the full evaluation would emit nothing, so skipping it changes no output bit. Most
+// voxels of a TSDF band are on one side of the surface with their whole neighbourhood.
+__device__ __forceinline__ bool halo_cell_is_empty(const float* s_sdf, const uint32_t* s_cw, int vi) {
+  const int x = vi & 7, y = (vi >> 3) & 7, z = vi >> 6; // halo cell (x + 1, y + 1, z + 1)
+  float lo = 3.4e38f, hi = -3.4e38f;
+  uint32_t w = 0;
+  bool finite = true;
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int c   = ((z + dz) * 10 + (y + dy)) * 10 + (x + dx);
+        const uint32_t wc = s_cw[c] >> 24;
+        if (wc) { // unobserved voxels never supply a value (see above)
+          const float v = s_sdf[c];
+          lo = fminf(lo, v), hi = fmaxf(hi, v);
+          finite &= fabsf(v) < 1e30f; // false for NaN too (fminf / fmaxf would drop it silently)
+        }
+        w |= wc;
+      }
+  if (!finite)
+    return false; // NaN / Inf / absurd payloads: let the full path decide
+  const float margin = 1e-4f * fmaxf(fabsf(lo), fabsf(hi));
+  return w == 0u || lo > margin || hi < -margin;
+}
+
+// One CTA of kMcThreads per live block. Small CTAs: per block the kernel is a chain of dependent
+// latencies (neighbour lookups -> halo fill -> filter -> cells -> append), so the SM is kept busy by
+// having many blocks in flight, not by wide CTAs idling at the barriers of one block.
+#ifndef MRH_MC_THREADS
+#define MRH_MC_THREADS 128
+#endif
+constexpr int kMcThreads = MRH_MC_THREADS;
+
 // force_generic: run every block through the hash sampler (validation of the halo path).
 // max_centers: only the first max_centers entries of the live list are meshed; the entries behind
 // them are ghost copies of other ranks' blocks (mrh_halo.cu), present only to be sampled.
-__global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, float* __restrict__ triangles, uint32_t* __restrict__ tri_count, uint32_t max_triangles, int force_generic, uint32_t max_centers) {
+__global__ void __launch_bounds__(kMcThreads, 1024 / kMcThreads) k_mc_blocks(MapDev m, uint32_t live_cur, float* __restrict__ triangles, uint32_t* __restrict__ tri_count, uint32_t max_triangles, int force_generic, uint32_t max_centers) {
   __shared__ float s_sdf[1000];
   __shared__ uint32_t s_cw[1000];
   __shared__ uint32_t s_nb[27];
   __shared__ int s_mixed;
-  __shared__ uint32_t s_warp_sum[8];
+  __shared__ uint32_t s_warp_sum[kMcThreads / 32];
   __shared__ uint32_t s_base;
+  __shared__ uint32_t s_n_cand;
+  __shared__ uint16_t s_cand[512];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_live = min(m.ctr->live_count[live_cur], max_centers);
   for (uint32_t li = blockIdx.x; li < n_live; li += gridDim.x) {
@@ -305,7 +355,7 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
     const i3 b         = unpack_key(key);
     const int res      = (int) (val >> 31);
     if (tid == 0)
-      s_mixed = res | force_generic;
+      s_mixed = res | force_generic, s_n_cand = 0;
     __syncthreads();
     if (tid < 27) {
       const i3 nb = {b.x + tid % 3 - 1, b.y + (tid / 3) % 3 - 1, b.z + tid / 9 - 1};
@@ -323,8 +373,10 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
     }
     __syncthreads();
     const bool generic = s_mixed != 0;
+    // the pre-filter's bounds assume voxel coordinates far below 2^23 (positions exact to vs / 16)
+    const bool prefilter = m.min_weight_threshold > 0 && max(max(abs(b.x), abs(b.y)), abs(b.z)) < (1 << 16);
     if (!generic) {
-      for (int c = tid; c < 1000; c += 256) {
+      for (int c = tid; c < 1000; c += kMcThreads) {
         const int i = c % 10, j = (c / 10) % 10, k = c / 100;
         const int bi = (i + 7) >> 3, bj = (j + 7) >> 3, bk = (k + 7) >> 3;
         const uint32_t v = s_nb[(bk * 3 + bj) * 3 + bi];
@@ -340,12 +392,29 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
       }
     }
     __syncthreads();
-    const int n_vox = res ? 64 : 512;
-    for (int pass = 0; pass < 2; ++pass) {
-      const int vi = pass * 256 + tid;
+    // Candidate cells of the block, compacted: the pre-filter drops most voxels of a TSDF band, and
+    // the survivors are packed so that whole warps take the full evaluation (a warp with one
+    // survivor among its 32 consecutive voxels would otherwise pay for all of it).
+    int n_vox = res ? 64 : 512;
+    if (!generic && prefilter) {
+      for (int vi = tid; vi < 512; vi += kMcThreads) {
+        const bool keep      = !halo_cell_is_empty(s_sdf, s_cw, vi);
+        const unsigned votes = __ballot_sync(0xFFFFFFFFu, keep);
+        uint32_t base        = 0;
+        if (lane == 0 && votes)
+          base = atomicAdd(&s_n_cand, (uint32_t) __popc(votes));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (keep)
+          s_cand[base + __popc(votes & ((1u << lane) - 1u))] = (uint16_t) vi;
+      }
+      __syncthreads();
+      n_vox = (int) s_n_cand;
+    }
+    for (int first = 0; first < n_vox; first += kMcThreads) {
       CellResult cell;
       cell.n_tri = 0;
-      if (vi < n_vox) {
+      if (first + tid < n_vox) {
+        const int vi = (!generic && prefilter) ? (int) s_cand[first + tid] : first + tid;
         const int sf = 1 << res, bs = 8 >> res;
         const i3 pi  = {b.x * 8 + sf * (vi % bs), b.y * 8 + sf * ((vi % (bs * bs)) / bs), b.z * 8 + sf * (vi / (bs * bs))};
         const f3 pf  = {fmul(i2f(pi.x), m.voxel_size), fmul(i2f(pi.y), m.voxel_size), fmul(i2f(pi.z), m.voxel_size)};
@@ -370,7 +439,7 @@ __global__ void __launch_bounds__(256) k_mc_blocks(MapDev m, uint32_t live_cur, 
       __syncthreads();
       if (tid == 0) {
         uint32_t tot = 0;
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < kMcThreads / 32; ++w) {
           const uint32_t t = s_warp_sum[w];
           s_warp_sum[w]    = tot;
           tot += t;

@@ -94,6 +94,35 @@ def test_halo_path_equals_generic_path():
     assert (ka == kb).all()
 
 
+def test_in_place_meshing_equals_round_trip(tmp_path, monkeypatch):
+    """A fully resident one-region map is meshed where it lies; MRH_MESH_ROUND_TRIP=1 forces the
+    reference's streamAllOut -> streamInToGPU -> streamAllOut sequence. Same soup, same host store,
+    same device state afterwards."""
+    a, _, _ = build_state(6, with_ref=False)
+    b, _, _ = build_state(6, with_ref=False)
+    blocks = a.getStats()["live_blocks"]
+    a.extractMesh(str(tmp_path / "a.ply"))
+    monkeypatch.setenv("MRH_MESH_ROUND_TRIP", "1")
+    b.extractMesh(str(tmp_path / "b.ply"))
+    monkeypatch.delenv("MRH_MESH_ROUND_TRIP")
+    ta, tb = a.getTriangles(), b.getTriangles()
+    assert len(ta) == len(tb) and len(ta) > 0
+    ka = np.sort(np.ascontiguousarray(ta.reshape(len(ta), -1)).view([("", ta.dtype)] * 18).ravel())
+    kb = np.sort(np.ascontiguousarray(tb.reshape(len(tb), -1)).view([("", tb.dtype)] * 18).ravel())
+    assert (ka == kb).all()
+    for g in (a, b):
+        st = g.getStats()
+        assert st["live_blocks"] == 0 and g.storeSize() == blocks
+        assert st["heap_free"] == NUM_BLOCKS
+    # and the map comes back from the store the same either way
+    a.serializeData(str(tmp_path / "ha.ply"), str(tmp_path / "va.ply"))
+    b.serializeData(str(tmp_path / "hb.ply"), str(tmp_path / "vb.ply"))
+    for name in ("v", "h"):
+        pa, ra = _ply_payload_sorted(str(tmp_path / f"{name}a.ply"))
+        pb, rb = _ply_payload_sorted(str(tmp_path / f"{name}b.ply"))
+        assert pa == pb and ra.shape == rb.shape and (ra == rb).all()
+
+
 def _read_ply_points(path):
     with open(path, "rb") as f:
         header = b""
