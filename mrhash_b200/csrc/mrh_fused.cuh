@@ -37,6 +37,7 @@ constexpr int kFuThreads = 128;
 constexpr int kFuWarps   = kFuThreads / 32;
 constexpr int kTileW     = 32; // one 128-byte depth row segment per bulk copy
 constexpr int kTileH     = 4;
+constexpr int kGcLocal   = 8; // condemned blocks a CTA removes itself on its way out; more go to the shared list
 constexpr int kSetCells  = 128; // per-tile set of resolved block keys
 constexpr unsigned long long kStatsOnly = 1ull << 63;
 constexpr unsigned long long kTerminator = ~0ull; // fusion-queue entry that releases a waiting CTA
@@ -123,6 +124,9 @@ struct FusedSmem {
   uint32_t warps_done; // warps of this CTA that have finished a chunk / tile item (every 4th completes an item)
   uint32_t n_items;    // chunks + tiles of the frame
   uint32_t rays;       // valid rays walked by this CTA
+  uint32_t vis_n;      // entries this CTA appended to the visible list (chunk items)
+  uint32_t gc_n;       // blocks this CTA has condemned (first kGcLocal of them in gc_local)
+  alignas(16) uint4 gc_local[kGcLocal]; // {table slot, pool block, output live index, -}
   alignas(16) uint4 peek[2]; // the scheduler's look at its next fusion-queue entry (cp.async target)
   int last;
 };
@@ -206,8 +210,10 @@ __device__ __forceinline__ void role_chunk(const MapDev& m, const FrameDev& f, c
   if (lane == 0) {
     if (am)
       abase = atomicAdd(&m.ctr->live_count[cur ^ 1u], (uint32_t) __popc(am));
-    if (vm)
+    if (vm) {
       vbase = atomicAdd(&m.ctr->vis_count, (uint32_t) __popc(vm));
+      atomicAdd(&sm.vis_n, (uint32_t) __popc(vm));
+    }
     if (qm)
       qbase = atomicAdd(&m.fqs->fq_count.v, (uint32_t) __popc(qm));
   }
@@ -350,6 +356,7 @@ __device__ __forceinline__ void warp_resolve(const MapDev& m, const CameraDev& c
           m.vis[vi] = e;
           fq_write(m, qi, f.tag, key, val, (uint32_t) free_slot, li, vi);
           atomicAdd(&m.ctr->blocks_new, 1ull);
+          atomicAdd(&m.ctr->blocks_visible, 1ull);
         }
       }
       __syncwarp();
@@ -805,9 +812,16 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
   if (tid == 0) {
     cta_updated += sm.red_upd[0] + sm.red_upd[1] + sm.red_upd[2] + sm.red_upd[3];
     if (del) {
-      // the block stays in the table until the finaliser: walkers of this frame must still find it
-      const uint32_t gi = atomicAdd(&m.fqs->gc_count.v, 1u);
-      m.gc_list[gi]     = {e.slot, val, e.live_idx, 0u};
+      // the block stays in the table until every walk of this frame is over: walkers must still find
+      // it. This CTA removes it on its way out (by then it has seen a terminator, which is written
+      // after the last tile); past kGcLocal blocks, the last CTA of the frame does.
+      const uint32_t k = sm.gc_n++;
+      if (k < (uint32_t) kGcLocal) {
+        sm.gc_local[k] = make_uint4(e.slot, val, e.live_idx, 0u);
+      } else {
+        const uint32_t gi = atomicAdd(&m.fqs->gc_count.v, 1u);
+        m.gc_list[gi]     = {e.slot, val, e.live_idx, 0u};
+      }
       st.min_abs_sdf    = 3.40282346638528859812e+38f;
       st.max_weight     = 0;
     }
@@ -999,7 +1013,7 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
     mbar_init(&sm.bar_depth[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    sm.last = 0, sm.warps_done = 0, sm.rays = 0;
+    sm.last = 0, sm.warps_done = 0, sm.rays = 0, sm.vis_n = 0, sm.gc_n = 0;
   }
   sm.set[0][tid] = kNoKey;
   sm.set[1][tid] = kNoKey;
@@ -1093,43 +1107,61 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
     DBG_MAX(3, t); // last CTA out of the loop
   }
 #endif
-  if (tid == 0) {
-    if (cta_updated)
-      atomicAdd(&m.ctr->voxels_updated, cta_updated);
-    if (sm.rays)
-      atomicAdd(&m.ctr->rays_valid, (unsigned long long) sm.rays);
-    __threadfence();
-    const unsigned done = atomicAdd(&m.fqs->done_ctas.v, 1u) + 1u;
-    sm.last             = done == gridDim.x ? 1 : 0;
-  }
-  __syncthreads();
-  if (!sm.last)
-    return;
-  __threadfence();
+  // deferred removal (garbageCollectFreeKernel + deleteHashEntryElement, :1727-1854): tombstone the
+  // key, push the pool block back on the free stack (appendHeapHigh :52-56), drop it from the live
+  // list. No walk is running any more, and nothing else of this frame looks at these three places.
   Counters* c    = m.ctr;
   FrameQueues* q = m.fqs;
-  // deferred removal (garbageCollectFreeKernel + deleteHashEntryElement, :1727-1854): tombstone the
-  // key, push the pool block back on the free stack (appendHeapHigh :52-56), drop it from the live list
-  const uint32_t n_gc = ld_vol(&q->gc_count.v);
-  for (uint32_t i = tid; i < n_gc; i += kFuThreads) {
-    const uint4 g = ld_vol_v4(m.gc_list + i);
+  const uint32_t n_mine = min(sm.gc_n, (uint32_t) kGcLocal);
+  if ((uint32_t) tid < n_mine) {
+    const uint4 g = sm.gc_local[tid];
     atomicExch(m.keys + g.x, kTomb);
     const int addr   = atomicAdd(&c->heap_counter, 1);
     m.heap[addr + 1] = g.y & 0x7FFFFFFFu;
     m.live[f.live_cur ^ 1u][g.z].slot = kInvalid;
   }
-  __syncthreads();
+  if (n_mine)
+    __syncthreads(); // (uniform) the pushes above have been performed before this CTA reports below
   if (tid == 0) {
-    atomicAdd(&c->blocks_visible, (unsigned long long) ld_vol(&c->vis_count));
-    if (n_gc)
-      atomicAdd(&c->blocks_freed, (unsigned long long) n_gc);
+    if (cta_updated)
+      atomicAdd(&c->voxels_updated, cta_updated);
+    if (sm.rays)
+      atomicAdd(&c->rays_valid, (unsigned long long) sm.rays);
+    if (sm.vis_n)
+      atomicAdd(&c->blocks_visible, (unsigned long long) sm.vis_n);
+    if (sm.gc_n)
+      atomicAdd(&c->blocks_freed, (unsigned long long) sm.gc_n);
+    __threadfence();
+    // one word tells the last CTA both that it is the last and whether any CTA spilled removals into
+    // the shared list (bit 16 and up), so that the common case ends without another round trip
+    const unsigned spill = sm.gc_n > (uint32_t) kGcLocal ? 0x10000u : 0u;
+    const unsigned done  = atomicAdd(&q->done_ctas.v, 1u + spill) + 1u + spill;
+    sm.last              = (done & 0xFFFFu) == gridDim.x ? (int) (1u + (done >> 16)) : 0;
+  }
+  __syncthreads();
+  if (!sm.last)
+    return;
+  // ---- the last CTA out re-arms the queues for the next frame ----
+  if (sm.last > 1) {
+    __threadfence();
+    const uint32_t n_gc = ld_vol(&q->gc_count.v);
+    for (uint32_t i = tid; i < n_gc; i += kFuThreads) {
+      const uint4 g = ld_vol_v4(m.gc_list + i);
+      atomicExch(m.keys + g.x, kTomb);
+      const int addr   = atomicAdd(&c->heap_counter, 1);
+      m.heap[addr + 1] = g.y & 0x7FFFFFFFu;
+      m.live[f.live_cur ^ 1u][g.z].slot = kInvalid;
+    }
+    __syncthreads();
+  }
+  if (tid < kQueueShards)
+    q->q_chunk[tid].v = 0, q->q_tile[tid].v = 0, q->q_fuse[tid].v = 0;
+  if (tid == 0) {
 #ifdef MRH_FUSED_DEBUG
     DBG_MAX(20, gtimer()); // finaliser done
     DBG_MAX(21, ld_vol(&q->fq_count.v));
     DBG_MAX(22, ld_vol(&q->q_tile[0].v));
 #endif
-    for (int i = 0; i < kQueueShards; ++i)
-      q->q_chunk[i].v = 0, q->q_tile[i].v = 0, q->q_fuse[i].v = 0;
     q->fq_count.v = 0, q->items_done.v = 0, q->gc_count.v = 0, q->done_ctas.v = 0;
     if (rearm) {
       c->live_count[f.live_cur] = 0; // next frame's output list
