@@ -43,6 +43,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
+STATS_LAG = 2  # e2e passes read every frame's counters this many frames after submitting it
 COUNTERS_BYTES = 144  # the part of mrh::Counters that getStats() / mrh_get_stats_pipelined read back
 
 
@@ -420,8 +421,8 @@ def main():
     host_us = {"setters": 0.0, "compute": 0.0, "read_result": 0.0}
     if world == 1:
         # streaming caller: page-locked frames are read by DMA while the previous frame's kernel runs
-        # (the frames of this pass are never modified), and every frame's counters reach the host one
-        # frame late instead of draining the device after each compute()
+        # (the frames of this pass are never modified), and every frame's counters reach the host two
+        # frames late instead of draining the device after each compute()
         g.setIngestMode(2)
         g.setStatsPipeline(True)
     e2e_state = {"n": 0}
@@ -436,9 +437,11 @@ def main():
             c1 = time.perf_counter()
             g.compute()
             c2 = time.perf_counter()
-            # D2H read of the step's result: the counters of the previous frame (its copy was enqueued
-            # behind that frame's kernel); the last frame's are read after the loop
-            st = g.getStatsPipelined(1) if e2e_state["n"] > 0 else None
+            # D2H read of a step's result: the counters of the frame submitted STATS_LAG steps ago (each
+            # frame's copy is enqueued behind its kernel); the last STATS_LAG frames' are read after the
+            # loop. With a lag of 2 the host never waits for the kernel it has just queued, so the
+            # upload of the next frame is submitted while the previous kernel is still running.
+            st = g.getStatsPipelined(STATS_LAG) if e2e_state["n"] >= STATS_LAG else None
             e2e_state["n"] += 1
             c3 = time.perf_counter()
             host_us["setters"] += c1 - c0
@@ -461,7 +464,7 @@ def main():
         g.setRGBImageDevice(bcast_c[b].data_ptr(), args.height, args.width)
         run_frame(g)
         ev_done[b].record(stream)
-        st = g.getStatsPipelined(1) if e2e_state["n"] > 0 else None  # the previous frame's counters: no drain
+        st = g.getStatsPipelined(STATS_LAG) if e2e_state["n"] >= STATS_LAG else None  # an earlier frame's counters: no drain
         e2e_state["n"] += 1
         return st
 
@@ -476,7 +479,8 @@ def main():
     t0 = time.perf_counter()
     for i in range(K):
         step_host(W + i)
-    last_stats = g.getStatsPipelined(0)  # the result of the last step (waits for that frame only)
+    for lag in range(STATS_LAG - 1, -1, -1):  # the results of the last steps (waits for those frames only)
+        last_stats = g.getStatsPipelined(lag)
     assert last_stats["frames"] >= K, last_stats
     e1.record(stream)
     g.synchronize()
@@ -509,11 +513,12 @@ def main():
             g.setDepthImage(depth_pg[i])
             g.setRGBImage(rgb_pg[i])
             g.compute()
-            if i:
-                g.getStatsPipelined(1)
-        g.getStatsPipelined(0)
+            if i >= STATS_LAG:
+                g.getStatsPipelined(STATS_LAG)
+        for lag in range(min(STATS_LAG, Kq) - 1, -1, -1):
+            g.getStatsPipelined(lag)
         dt = time.perf_counter() - t0
-        e2e_pageable = {"value": Kq / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / Kq, "steps": Kq, "what": "inputs in pageable host memory (what rgbd_runner.py hands over): copied into pinned staging inside the setters (default ingest mode), counters read one frame late"}
+        e2e_pageable = {"value": Kq / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / Kq, "steps": Kq, "what": "inputs in pageable host memory (what rgbd_runner.py hands over): copied into pinned staging inside the setters (default ingest mode), counters read two frames late"}
         g.close()
 
     # ---------------- N > 1 only: (i) one independent stream per GPU, (ii) sharded meshing ------------
@@ -662,7 +667,7 @@ def main():
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
             "value_kind": "device time: CUDA events around each compute(), device-resident inputs, L2 flushed before every step",
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()},
-                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back one frame late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers (overlaps the previous frame's kernels), counters of every frame read back one frame late"},
+                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back two frames late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers (overlaps the previous frame's kernels), counters of every frame read back two frames late"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
             "kernels": per_kernel,

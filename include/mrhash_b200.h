@@ -217,10 +217,11 @@ int mrh_set_field(mrh_map* m, const char* name, double value);
 
 int mrh_get_stats(mrh_map* m, mrh_stats* out);
 /* Statistics without a stall per frame: once enabled, every mrh_compute() is followed by an asynchronous
- * copy of the counters into page-locked memory; mrh_get_stats_pipelined(which = 1) returns the state
- * after the frame BEFORE the last compute() (already there: no wait), which = 0 the state after the
- * last one (waits for that frame only). A caller that reads which = 1 after every compute() sees every
- * frame's result, one frame late, and never drains the device. */
+ * copy of the counters into one of four page-locked slots; mrh_get_stats_pipelined(which = k) returns
+ * the state after the frame k compute() calls before the last one (k = 0 .. 3; it waits for that frame
+ * only). A caller that reads which = 2 after every compute() sees every frame's result two frames late
+ * and never waits for a kernel it has just queued, so the next frame's upload is submitted while the
+ * previous frame is still on the device. */
 int mrh_set_stats_pipeline(mrh_map* m, int enabled);
 int mrh_get_stats_pipelined(mrh_map* m, int which, mrh_stats* out);
 int mrh_reset_stats(mrh_map* m);

@@ -133,7 +133,7 @@ static void free_map(mrh_map* m) {
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
   cudaFreeHost(m->h_ctr_ring);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < mrh_map::kCtrRing; ++i)
     if (m->ev_ctr[i])
       cudaEventDestroy(m->ev_ctr[i]);
   cudaFreeHost(m->h_heap_probe);
@@ -627,11 +627,11 @@ static int compute_frame(mrh_map* m) {
       in->pending_direct = false;
     }
   if (m->stats_pipeline) {
-    m->ctr_slot ^= 1;
+    m->ctr_slot = (m->ctr_slot + 1) % mrh_map::kCtrRing;
     CK(cudaMemcpyAsync(m->h_ctr_ring + m->ctr_slot, m->dev.ctr, offsetof(Counters, dbg), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaEventRecord(m->ev_ctr[m->ctr_slot], m->stream));
     m->ctr_frames[m->ctr_slot] = m->frames_total;
-    m->ctr_filled              = std::min(m->ctr_filled + 1, 2);
+    m->ctr_filled              = std::min(m->ctr_filled + 1, (int) mrh_map::kCtrRing);
   }
   return 0;
 }
@@ -805,8 +805,8 @@ int mrh_set_ingest_mode(mrh_map* m, int mode) {
 int mrh_set_stats_pipeline(mrh_map* m, int enabled) {
   GUARD(m);
   if (enabled && !m->h_ctr_ring) {
-    CK(cudaMallocHost(&m->h_ctr_ring, 2 * sizeof(Counters)));
-    for (int i = 0; i < 2; ++i)
+    CK(cudaMallocHost(&m->h_ctr_ring, mrh_map::kCtrRing * sizeof(Counters)));
+    for (int i = 0; i < mrh_map::kCtrRing; ++i)
       CK(cudaEventCreateWithFlags(&m->ev_ctr[i], cudaEventDisableTiming));
   }
   m->stats_pipeline = enabled != 0;
@@ -820,13 +820,14 @@ int mrh_get_stats_pipelined(mrh_map* m, int which, mrh_stats* out) {
     return fail("null argument");
   if (!m->stats_pipeline)
     return fail("mrh_get_stats_pipelined: enable mrh_set_stats_pipeline first");
-  // which = 1: the frame before the last compute() (its copy has normally landed: no wait);
-  // which = 0: the last compute() (waits for that frame)
-  if (which != 0 && which != 1)
-    return fail("mrh_get_stats_pipelined: which must be 0 or 1");
+  // which = 0: the last compute() (waits for that frame); which = k: k frames earlier. A caller that
+  // reads frame n - 2 after submitting frame n never waits for a kernel it has just queued, so the
+  // upload of frame n + 1 can be submitted while frame n - 1 is still on the device.
+  if (which < 0 || which >= mrh_map::kCtrRing)
+    return fail("mrh_get_stats_pipelined: which must be 0 .. %d", mrh_map::kCtrRing - 1);
   if (m->ctr_filled < 1 + which)
     return fail("mrh_get_stats_pipelined: no such frame yet");
-  const int slot = m->ctr_slot ^ which;
+  const int slot = (m->ctr_slot - which + mrh_map::kCtrRing) % mrh_map::kCtrRing;
   CK(cudaEventSynchronize(m->ev_ctr[slot]));
   return fill_stats(m, m->h_ctr_ring[slot], m->ctr_frames[slot], out);
 }

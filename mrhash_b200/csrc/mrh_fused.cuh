@@ -516,6 +516,18 @@ __device__ __forceinline__ void role_tile(const MapDev& m, const FrameDev& f, co
         skip = __all_sync(full, present);
       }
     }
+#ifdef MRH_FUSED_DEBUG
+    if (lane == 0 && !skip) { // why is this patch walked?
+      DBG_ADD(29, 1);
+      if (!all_fast)
+        DBG_ADD(18, 1);
+      else {
+        const unsigned nx = (unsigned) (hix - lox) + 1u, ny = (unsigned) (hiy - loy) + 1u, nz = (unsigned) (hiz - loz) + 1u;
+        const bool fits = (nz <= 2u && nx <= 4u && ny <= 4u) || (ny <= 2u && nx <= 4u && nz <= 4u) || (nx <= 2u && ny <= 4u && nz <= 4u);
+        DBG_ADD(fits ? 28 : 19, 1);
+      }
+    }
+#endif
     if (skip) {
       const unsigned n_skipped = __popc(__ballot_sync(full, active));
       if (lane == 0 && n_skipped)

@@ -134,12 +134,13 @@ struct mrh_map {
   int ingest_mode = 0;
   // pipelined statistics (mrh_set_stats_pipeline): every compute() is followed by an asynchronous copy
   // of the counters into one of two pinned slots; mrh_get_stats_pipelined returns the previous frame's
-  mrh::Counters* h_ctr_ring = nullptr; // 2 pinned slots
-  cudaEvent_t ev_ctr[2]{};
-  uint64_t ctr_frames[2]{};            // frames_total at the time of the copy
+  static constexpr int kCtrRing = 4;
+  mrh::Counters* h_ctr_ring = nullptr; // kCtrRing pinned slots
+  cudaEvent_t ev_ctr[kCtrRing]{};
+  uint64_t ctr_frames[kCtrRing]{};     // frames_total at the time of the copy
   bool stats_pipeline = false;
   int ctr_slot        = 0;             // slot of the most recent compute()
-  int ctr_filled      = 0;             // copies issued so far (0, 1, 2+)
+  int ctr_filled      = 0;             // copies issued so far (saturates at kCtrRing)
 
   // optional per-kernel timing (bench.py roofline pass): events between the kernels of a frame
   bool profiling = false;

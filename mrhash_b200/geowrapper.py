@@ -372,7 +372,7 @@ class GeoWrapper:
         check(self._lib.mrh_set_stats_pipeline(self._h, 1 if enabled else 0))
 
     def getStatsPipelined(self, which=1):
-        """Counters after the frame before the last compute() (which=1, no wait) or after the last one (which=0)."""
+        """Counters after the frame `which` compute() calls before the last one (0 .. 3; waits for that frame only)."""
         s = _capi.Stats()
         check(self._lib.mrh_get_stats_pipelined(self._h, int(which), C.byref(s)))
         return s.as_dict()

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Tuning build: tools/build_variant.sh <name> <extra nvcc flags...>  ->  mrhash_b200/libmrhash_b200_<name>.so
 # (use with MRH_LIB=... ; the product build is mrhash_b200/build.sh)
-set -e
+set -e -o pipefail
 cd "$(dirname "$0")/../mrhash_b200/csrc"
 NAME=$1; shift
 mkdir -p ../_build_$NAME

@@ -35,6 +35,7 @@ for k in range(n):
             cnt = max(v[8 + r], 1)
             print(f"   {names[r]:5s}: items {v[8+r]:6d} sum {v[4+r]/1e3:9.1f} us  mean {v[4+r]/cnt/1e3:7.2f} us  last ended +{us(v[12+r]):.1f} us  longest {v[24+r]/1e3:.1f} us")
         print(f"   sched: sum {v[16]/1e3:.1f} us max {v[17]/1e3:.1f} us")
+        print(f"   walked patches {v[29]}: ray off the fast path {v[18]}, box too large {v[19]}, block missing {v[28]}")
     if k == n - 1:
         ntr = min(int(v[30]), 8192)
         tb = (C.c_uint64 * (2 * ntr))()
