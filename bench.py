@@ -411,6 +411,7 @@ def main():
     bcast = [torch.empty(7 * P, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     bcast_d = [b[: 4 * P].view(torch.float32).view(args.height, args.width) for b in bcast] if world > 1 else None
     bcast_c = [b[4 * P :].view(args.height, args.width, 3) for b in bcast] if world > 1 else None
+    scatter = world > 1 and args.height % world == 0 and os.environ.get("MRH_BENCH_INGEST", "scatter") != "broadcast"
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
     for e in ev_done:
@@ -454,10 +455,15 @@ def main():
         b = e2e_state["n"] & 1
         g.setCurrPose(*poses[k])
         torch.cuda.current_stream().wait_event(ev_done[b])
-        if rank == 0:
-            bcast_d[b].copy_(depth_h[k], non_blocking=True)
-            bcast_c[b].copy_(rgb_h[k], non_blocking=True)
-        dist.broadcast(bcast[b], 0)
+        if scatter:
+            # every rank uploads its band of rows over its own PCIe link; an in-place all-gather over
+            # NVLink completes the frame everywhere (sharding.scatter_ingest_frame)
+            sharding.scatter_ingest_frame(bcast_d[b], bcast_c[b], depth_h[k], rgb_h[k])
+        else:
+            if rank == 0:
+                bcast_d[b].copy_(depth_h[k], non_blocking=True)
+                bcast_c[b].copy_(rgb_h[k], non_blocking=True)
+            dist.broadcast(bcast[b], 0)
         ev_ready[b].record()
         stream.wait_event(ev_ready[b])
         g.setDepthImageDevice(bcast_d[b].data_ptr(), args.height, args.width)
@@ -657,7 +663,7 @@ def main():
                 "num_sdf_blocks": NUM_SDF_BLOCKS,
                 "hash_num_buckets": HASH_NUM_BUCKETS,
                 "l2": "flushed before every step (256 MiB memset, excluded from the per-step CUDA-event window)",
-                "parallelism": "1 GPU" if world == 1 else f"map sharded by hash-bucket range over {world} GPUs, frame broadcast over NCCL",
+                "parallelism": "1 GPU" if world == 1 else f"map sharded by hash-bucket range over {world} GPUs; e2e: frame " + ("uploaded in row bands by all ranks + NCCL all-gather" if scatter else "uploaded by rank 0 + NCCL broadcast"),
             },
             "mvoxels_updated_per_sec": v_upd / (ms_flushed * 1e-3) / 1e6,
             "voxels_updated_per_frame": v_upd / K,
@@ -667,7 +673,7 @@ def main():
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
             "value_kind": "device time: CUDA events around each compute(), device-resident inputs, L2 flushed before every step",
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()},
-                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back two frames late (mrh_get_stats_pipelined)" if world == 1 else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers (overlaps the previous frame's kernels), counters of every frame read back two frames late"},
+                    "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back two frames late (mrh_get_stats_pipelined)" if world == 1 else ("every rank uploads its band of rows from page-locked host memory over its own PCIe link, in-place NCCL all-gather over NVLink completes the frame on every rank (sharding.scatter_ingest_frame), alternating buffers" if scatter else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers") + " (overlaps the previous frame's kernels), counters of every frame read back two frames late"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
             "kernels": per_kernel,

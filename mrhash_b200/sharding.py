@@ -54,6 +54,41 @@ def broadcast_frame(depth, rgb, pose, src=0, group=None):
     dist.broadcast(rgb, src, group=group)
 
 
+def frame_row_band(rank, world, rows):
+    """Rows [lo, hi) of a frame that `rank` uploads in scatter_ingest_frame (equal bands; rows % world == 0)."""
+    band = rows // world
+    return rank * band, (rank + 1) * band
+
+
+def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None):
+    """Upload ONE frame to all ranks of a node without sending it down one PCIe link `world` times.
+
+    Every rank maps the same host frame (one shared, page-locked segment in a server; in bench.py every
+    rank's own copy of the synthetic stream) and uploads only its band of rows over ITS OWN PCIe link,
+    straight into its place in the full device image; an in-place all-gather over NVLink / NVSwitch then
+    completes the image on every rank. Host -> device bytes per rank: 1 / world of the frame; the
+    collective moves the frame at NVLink rate. Runs on the current torch stream; the caller orders the
+    handle's stream after it (events), as with broadcast_frame.
+    depth_dev f32 [H,W] and rgb_dev u8 [H,W,3]: device, contiguous; *_host: the same shapes, pinned."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        depth_dev.copy_(depth_host, non_blocking=True)
+        rgb_dev.copy_(rgb_host, non_blocking=True)
+        return
+    rank = dist.get_rank(group)
+    rows = depth_dev.shape[0]
+    if rows % world:
+        raise ValueError(f"scatter_ingest_frame: {rows} rows do not split into {world} equal bands")
+    lo, hi = frame_row_band(rank, world, rows)
+    depth_dev[lo:hi].copy_(depth_host[lo:hi], non_blocking=True)
+    rgb_dev[lo:hi].copy_(rgb_host[lo:hi], non_blocking=True)
+    # in place: each rank's input is its own band of the output (NCCL's in-place all-gather layout)
+    dist.all_gather_into_tensor(depth_dev.view(-1), depth_dev[lo:hi].reshape(-1), group=group)
+    dist.all_gather_into_tensor(rgb_dev.view(-1), rgb_dev[lo:hi].reshape(-1), group=group)
+
+
 def compute_sharded(geo, group=None):
     """compute() of one rank of a sharded map. Integration itself needs no exchange; the exception is
     the starve frame (every n_frames_invalidate_voxels-th): the per-pixel front-most voxel has to be the

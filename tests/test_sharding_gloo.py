@@ -31,6 +31,13 @@ def _worker(rank, world, port, out):
         t, q, depth, rgb = synth.rgbd_frame(3, n_frames=100, width=64, height=48)
         assert np.array_equal(d.numpy(), depth) and np.array_equal(c.numpy(), rgb)
         assert np.array_equal(p.numpy(), np.concatenate([t, q]).astype(np.float32))
+        # 1b. scatter ingest: every rank uploads only its band of rows, the in-place all-gather completes the frame
+        dd, cc = torch.zeros((48, 64)), torch.zeros((48, 64, 3), dtype=torch.uint8)
+        lo, hi = sharding.frame_row_band(rank, world, 48)
+        host_d, host_c = torch.zeros((48, 64)), torch.zeros((48, 64, 3), dtype=torch.uint8)
+        host_d[lo:hi], host_c[lo:hi] = torch.from_numpy(depth)[lo:hi], torch.from_numpy(rgb)[lo:hi]  # the rest is never read
+        sharding.scatter_ingest_frame(dd, cc, host_d, host_c)
+        assert np.array_equal(dd.numpy(), depth) and np.array_equal(cc.numpy(), rgb)
         # 2. each rank "owns" the blocks of its bucket range; gathering them on rank 0 restores the set
         rng = np.random.default_rng(0)
         blocks = np.unique(rng.integers(-40, 40, size=(500, 3)), axis=0).astype(np.int32)
