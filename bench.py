@@ -349,6 +349,16 @@ def main():
     for k in range(W):
         step_device(k)
     g.synchronize()
+    if world > 1:
+        # The only collective on the integration path is the z-buffer min-reduction of a starve frame
+        # (every n_frames_invalidate_voxels-th frame: none falls into the warm-up). NCCL sets up the
+        # channels of a (collective, size) pair on first use - tens of milliseconds at 8 ranks - so that
+        # first use happens here, not inside a timed step.
+        zb = torch.full((P,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            dist.all_reduce(zb, op=dist.ReduceOp.MIN)
+        del zb
+        barrier()
     g.resetStats()
     launches0 = g.launchCount()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -412,6 +422,7 @@ def main():
     bcast_d = [b[: 4 * P].view(torch.float32).view(args.height, args.width) for b in bcast] if world > 1 else None
     bcast_c = [b[4 * P :].view(args.height, args.width, 3) for b in bcast] if world > 1 else None
     scatter = world > 1 and args.height % world == 0 and os.environ.get("MRH_BENCH_INGEST", "scatter") != "broadcast"
+    scatter_views = [sharding.scatter_views(bcast_d[b], bcast_c[b]) for b in range(2)] if scatter else None
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
     for e in ev_done:
@@ -458,7 +469,7 @@ def main():
         if scatter:
             # every rank uploads its band of rows over its own PCIe link; an in-place all-gather over
             # NVLink completes the frame everywhere (sharding.scatter_ingest_frame)
-            sharding.scatter_ingest_frame(bcast_d[b], bcast_c[b], depth_h[k], rgb_h[k])
+            sharding.scatter_ingest_frame(bcast_d[b], bcast_c[b], depth_h[k], rgb_h[k], views=scatter_views[b])
         else:
             if rank == 0:
                 bcast_d[b].copy_(depth_h[k], non_blocking=True)

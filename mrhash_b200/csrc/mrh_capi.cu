@@ -129,6 +129,8 @@ static void free_map(mrh_map* m) {
     }
   if (m->copy_stream)
     cudaStreamDestroy(m->copy_stream);
+  if (m->copy_stream2)
+    cudaStreamDestroy(m->copy_stream2);
   cudaFree(m->d_tri), cudaFree(m->d_tri_count), cudaFree(m->d_soup_acc), cudaFree(m->d_shell_idx);
   cudaFree(m->d_upd_keys[0]), cudaFree(m->d_upd_keys[1]), cudaFree(m->d_upd_vals[0]), cudaFree(m->d_upd_vals[1]), cudaFree(m->d_sort_tmp);
   cudaFreeHost(m->h_ctr);
@@ -241,7 +243,7 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
     CK(cudaMalloc(&in.d_buf[w], bytes));
     in.d_cap[w] = bytes;
   }
-  CK(cudaStreamWaitEvent(m->copy_stream, in.consumed[w], 0));
+  CK(cudaStreamWaitEvent(in.stream, in.consumed[w], 0));
   bool direct = false;
   if (src_or_null && m->ingest_mode != 0) {
     cudaPointerAttributes attr;
@@ -253,8 +255,8 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
     // which the caller may reuse from now on (the contract of mrh_set_ingest_mode)
     if (m->ingest_mode == 2)
       CK(cudaEventSynchronize(in.copied[w]));
-    CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, m->copy_stream));
-    CK(cudaEventRecord(in.copied[w], m->copy_stream));
+    CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, in.stream));
+    CK(cudaEventRecord(in.copied[w], in.stream));
     in.pending_direct = true;
   } else {
     if (bytes > in.h_cap[w]) {
@@ -266,8 +268,8 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
     }
     CK(cudaEventSynchronize(in.copied[w])); // the transfer that last read this staging buffer has finished
     fill((T*) in.h_buf[w]);
-    CK(cudaMemcpyAsync(in.d_buf[w], in.h_buf[w], bytes, cudaMemcpyHostToDevice, m->copy_stream));
-    CK(cudaEventRecord(in.copied[w], m->copy_stream));
+    CK(cudaMemcpyAsync(in.d_buf[w], in.h_buf[w], bytes, cudaMemcpyHostToDevice, in.stream));
+    CK(cudaEventRecord(in.copied[w], in.stream));
   }
   in.which  = w;
   in.active = true;
@@ -323,6 +325,9 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   CK(cudaEventCreate(&m->ev0));
   CK(cudaEventCreate(&m->ev1));
   CK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&m->copy_stream2, cudaStreamNonBlocking));
+  m->in_depth.stream = m->in_points.stream = m->copy_stream;
+  m->in_rgb.stream = m->in_normals.stream = getenv("MRH_ONE_COPY_STREAM") ? m->copy_stream : m->copy_stream2;
   for (Ingest* in : {&m->in_depth, &m->in_rgb, &m->in_points, &m->in_normals})
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&in->copied[i], cudaEventDisableTiming));

@@ -50,9 +50,10 @@ FrameDev make_frame(const mrh_map* m) {
   }
   f.frame_index = m->frame_index;
   f.live_cur    = m->live_cur;
-  // paging probe wanted this frame? (a write to host memory delays the end of the kernel by ~1.5 us)
-  const bool pool_low = (double) (((volatile int*) m->h_heap_probe)[0] + 1) < 0.4 * (double) m->num_sdf_blocks;
-  f.pad[0] = m->stream_threshold > 0.f && ((m->frame_index & 15u) == 0 || pool_low) ? 1u : 0u;
+  // paging probe: every frame while paging is enabled, as the reference looks at the free count in
+  // front of every integrate (geowrapper.cpp:137). The write to host memory delays the end of the
+  // kernel by ~1.5 us; a map that never pages (stream_threshold = 0) does not pay it.
+  f.pad[0] = m->stream_threshold > 0.f ? 1u : 0u;
   f.pad[1] = 0;
   return f;
 }

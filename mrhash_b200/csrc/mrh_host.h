@@ -77,6 +77,7 @@ namespace mrh {
     int which   = 0;
     bool active = false; // d_buf[which] holds the current frame's data
     bool pending_direct = false; // a transfer straight from the caller's pinned memory is in flight
+    cudaStream_t stream = nullptr; // the copy stream this input travels on (depth / points: 0, colour / normals: 1)
   };
 
 } // namespace mrh
@@ -98,7 +99,8 @@ struct mrh_map {
 
   // ingest: copies run on their own stream into double-buffered device images, so the transfer of
   // frame k+1 overlaps the kernels of frame k (mrh_capi.cu: struct use in ingest_upload)
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of depth images / points
+  cudaStream_t copy_stream2 = nullptr; // H2D of colour images / normals: the two uploads of a frame overlap their fixed costs
   mrh::Ingest in_depth, in_rgb, in_points, in_normals;
   const float* depth_ptr = nullptr;
   const uint8_t* rgb_ptr = nullptr;

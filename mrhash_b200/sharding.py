@@ -60,7 +60,22 @@ def frame_row_band(rank, world, rows):
     return rank * band, (rank + 1) * band
 
 
-def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None):
+def scatter_views(depth_dev, rgb_dev, group=None):
+    """The tensor views scatter_ingest_frame needs for one pair of device images, built once by a caller
+    that reuses its images (a per-frame loop then spends its host time on the copies and collectives only)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    rows = depth_dev.shape[0]
+    if rows % world:
+        raise ValueError(f"scatter_ingest_frame: {rows} rows do not split into {world} equal bands")
+    lo, hi = frame_row_band(rank, world, rows)
+    return {"lo": lo, "hi": hi, "d_band": depth_dev[lo:hi], "c_band": rgb_dev[lo:hi], "d_all": depth_dev.view(-1), "c_all": rgb_dev.view(-1),
+            "d_in": depth_dev[lo:hi].reshape(-1), "c_in": rgb_dev[lo:hi].reshape(-1)}
+
+
+def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None, views=None):
     """Upload ONE frame to all ranks of a node without sending it down one PCIe link `world` times.
 
     Every rank maps the same host frame (one shared, page-locked segment in a server; in bench.py every
@@ -69,7 +84,8 @@ def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None):
     completes the image on every rank. Host -> device bytes per rank: 1 / world of the frame; the
     collective moves the frame at NVLink rate. Runs on the current torch stream; the caller orders the
     handle's stream after it (events), as with broadcast_frame.
-    depth_dev f32 [H,W] and rgb_dev u8 [H,W,3]: device, contiguous; *_host: the same shapes, pinned."""
+    depth_dev f32 [H,W] and rgb_dev u8 [H,W,3]: device, contiguous; *_host: the same shapes, pinned.
+    views: scatter_views(depth_dev, rgb_dev), for callers that reuse their device images."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -77,16 +93,13 @@ def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None):
         depth_dev.copy_(depth_host, non_blocking=True)
         rgb_dev.copy_(rgb_host, non_blocking=True)
         return
-    rank = dist.get_rank(group)
-    rows = depth_dev.shape[0]
-    if rows % world:
-        raise ValueError(f"scatter_ingest_frame: {rows} rows do not split into {world} equal bands")
-    lo, hi = frame_row_band(rank, world, rows)
-    depth_dev[lo:hi].copy_(depth_host[lo:hi], non_blocking=True)
-    rgb_dev[lo:hi].copy_(rgb_host[lo:hi], non_blocking=True)
+    v = views if views is not None else scatter_views(depth_dev, rgb_dev, group)
+    lo, hi = v["lo"], v["hi"]
+    v["d_band"].copy_(depth_host[lo:hi], non_blocking=True)
+    v["c_band"].copy_(rgb_host[lo:hi], non_blocking=True)
     # in place: each rank's input is its own band of the output (NCCL's in-place all-gather layout)
-    dist.all_gather_into_tensor(depth_dev.view(-1), depth_dev[lo:hi].reshape(-1), group=group)
-    dist.all_gather_into_tensor(rgb_dev.view(-1), rgb_dev[lo:hi].reshape(-1), group=group)
+    dist.all_gather_into_tensor(v["d_all"], v["d_in"], group=group)
+    dist.all_gather_into_tensor(v["c_all"], v["c_in"], group=group)
 
 
 def compute_sharded(geo, group=None):
@@ -214,7 +227,11 @@ def halo_exchange(geo, group=None):
     records = geo.haloPack(asked, full)
     got, got_counts = _all_to_all_rows(records, asked_counts, group)  # answers, in the order I asked
     assert got_counts == [int(c) for c in send_counts] and len(got) == len(req)
-    geo.haloInsert(req, got, full)
+    try:
+        geo.haloInsert(req, got, full)
+    except Exception:
+        geo.haloClear()  # a partial insert must not leave ghost blocks (or the "exchange active" state) behind
+        raise
     return {"requested": int(len(req)), "served": int(len(asked)), "full_blocks": full, "bytes_received": int(got.numel()), "bytes_sent": int(records.numel())}
 
 
