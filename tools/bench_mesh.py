@@ -15,7 +15,20 @@ import torch
 from mrhash_b200 import GeoWrapper, synth
 
 
-def run(target=97657, voxel=0.003, with_ref=False, log=None):
+def triangle_fingerprints(tris):
+    """One 64-bit value per triangle from its 72 bytes (order of the three vertices kept, as both
+    implementations emit them): equal sorted fingerprint arrays = the same multiset of bit-identical
+    triangles, up to a 2^-64 collision chance per pair."""
+    w = np.ascontiguousarray(tris, dtype=np.float32).reshape(len(tris), 18).view(np.uint32).astype(np.uint64)
+    h = np.zeros(len(tris), np.uint64)
+    with np.errstate(over="ignore"):
+        for j in range(18):
+            h = (h ^ w[:, j]) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(j + 1)
+            h ^= h >> np.uint64(29)
+    return np.sort(h)
+
+
+def run(target=97657, voxel=0.003, with_ref=False, log=None, compare=False):
     w, h = 1280, 960
     p = dict(synth.REPLICA_PARAMS)
     p["virtual_voxel_size"] = voxel
@@ -55,14 +68,21 @@ def run(target=97657, voxel=0.003, with_ref=False, log=None):
         t0 = time.perf_counter()
         n_ref = ref.lib.ref_extract_triangles(ref.h, None, 0)
         ref_info = {"ref_kernel_and_d2h_s": time.perf_counter() - t0, "ref_triangles": int(n_ref)}
+        if compare:
+            ref_tris, _ = ref.extract_triangles(int(n_ref))
+            ref_fp = triangle_fingerprints(ref_tris)
+            del ref_tris
         del ref
-    t0 = time.perf_counter()
-    g.streamAllOut()
-    t_out = time.perf_counter() - t0
+    # the call sequence of rgbd_runner.py: extractMesh on the resident map, then serializeData
     t0 = time.perf_counter()
     g.extractMesh("/tmp/mesh_bench.ply")
     t_mesh = time.perf_counter() - t0
     tris, V, F = g.getTriangles(), g.getVertices(), g.getFaces()
+    if ref_info is not None and compare:
+        fp = triangle_fingerprints(tris)
+        same = len(fp) == len(ref_fp) and bool((fp == ref_fp).all())
+        ref_info["bit_identical_triangles"] = len(fp) if same else int(np.isin(fp, ref_fp).sum())
+
     t0 = time.perf_counter()
     g.serializeData("/tmp/hash_bench.ply", "/tmp/voxel_bench.ply")
     t_ser = time.perf_counter() - t0
@@ -78,7 +98,7 @@ def run(target=97657, voxel=0.003, with_ref=False, log=None):
         "vertices": len(V),
         "faces": len(F),
         "build_s": build_s,
-        "stream_all_out_s": t_out,
+        "stream_all_out_s": breakdown["LastMeshStreamMs"] / 1e3,  # the copy of the resident map into the host store inside extractMesh
         "extract_mesh_total_s": t_mesh,
         "mesh_breakdown_ms": breakdown,
         "mc_kernel_algorithmic_bytes": algo,
@@ -97,4 +117,4 @@ def run(target=97657, voxel=0.003, with_ref=False, log=None):
 
 
 if __name__ == "__main__":
-    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 97657, float(sys.argv[2]) if len(sys.argv) > 2 else 0.003, os.environ.get("MRH_BENCH_REF", "0") == "1", log=lambda s: print(s, file=sys.stderr, flush=True))))
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 97657, float(sys.argv[2]) if len(sys.argv) > 2 else 0.003, os.environ.get("MRH_BENCH_REF", "0") == "1", compare=os.environ.get("MRH_BENCH_COMPARE", "0") == "1", log=lambda s: print(s, file=sys.stderr, flush=True))))
