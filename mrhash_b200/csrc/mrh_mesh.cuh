@@ -48,6 +48,7 @@ __device__ __forceinline__ VoxVal read_voxel_addr(const MapDev& m, unsigned long
 }
 
 struct HashSampler {
+  static constexpr bool kRollCorners = false;
   const MapDev& m;
   __device__ __forceinline__ bool block_val(i3 b, uint32_t& val) const {
     const int slot = table_find(m, b);
@@ -89,7 +90,11 @@ struct HashSampler {
 
 // ---- shared-memory sampler: 10^3 halo around one resolution-0 block whose 27-neighbourhood holds
 // no resolution-1 block (so every voxel size query answers the base size) ------------------------
+#ifndef MRH_MC_ROLL
+#define MRH_MC_ROLL 1
+#endif
 struct HaloSampler {
+  static constexpr bool kRollCorners = MRH_MC_ROLL != 0;
   const MapDev& m;
   const float* s_sdf;   // [1000]
   const uint32_t* s_cw; // [1000]
@@ -221,18 +226,32 @@ __device__ __forceinline__ void mc_cell(const S& s, const MapDev& m, f3 pf, Cell
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  auto corner = [&](int k) -> bool {
     const f3 p = {fadd(pf.x, (k & 1) ? sp[0] : sm[0]), fadd(pf.y, (k & 2) ? sp[1] : sm[1]), fadd(pf.z, (k & 4) ? sp[2] : sm[2])};
     float dist;
     const bool valid = trilinear(s, p, dist);
     const VoxVal v   = s.voxel_point(p, nullptr);
     if (!valid) {
       if ((int) (v.cw >> 24) < m.min_weight_threshold)
-        return;
+        return false;
       dist = v.sdf;
     }
     out.p[k] = p, out.d[k] = dist, out.cw[k] = v.cw;
+    return true;
+  };
+  if (S::kRollCorners) {
+    // one copy of the corner evaluation instead of eight: unrolled, the shared-memory path is ~4 000
+    // straight-line instructions and the few warps a block keeps after the pre-filter wait on
+    // instruction fetch; the cell's arrays live in local memory either way (mc_emit indexes them)
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k)
+      if (!corner(k))
+        return;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (!corner(k))
+        return;
   }
   unsigned cube = 0;
 #pragma unroll
