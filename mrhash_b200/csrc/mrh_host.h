@@ -8,11 +8,6 @@
 
 #include <cuda_runtime.h>
 
-#include <sys/mman.h>
-
-#include <cstdlib>
-#include <new>
-
 #include "../../include/mrhash_b200.h"
 #include "mrh_types.cuh"
 
@@ -30,27 +25,6 @@ namespace mrh {
     NoInitAlloc() = default;
     template <typename U>
     NoInitAlloc(const NoInitAlloc<U>&) {
-    }
-    // Large blocks come 2 MB-aligned and are offered to the kernel as transparent huge pages: a
-    // 600 MB store is then ~300 page faults instead of ~150 000 (first touch was most of streamAllOut).
-    static constexpr size_t kHugeAlign = size_t(2) << 20, kHugeMin = size_t(8) << 20;
-    T* allocate(size_t n) {
-      const size_t bytes = n * sizeof(T);
-      if (bytes >= kHugeMin) {
-        void* p = nullptr;
-        if (posix_memalign(&p, kHugeAlign, (bytes + kHugeAlign - 1) / kHugeAlign * kHugeAlign) == 0) {
-          madvise(p, bytes, MADV_HUGEPAGE); // a hint: ignored where THP is off
-          return static_cast<T*>(p);
-        }
-        throw std::bad_alloc();
-      }
-      return static_cast<T*>(::operator new(bytes));
-    }
-    void deallocate(T* p, size_t n) noexcept {
-      if (n * sizeof(T) >= kHugeMin)
-        free(p);
-      else
-        ::operator delete(p);
     }
     template <typename U>
     void construct(U* p) {
