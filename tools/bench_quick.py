@@ -35,4 +35,4 @@ def run(flushed):
     return 1e3 * float(np.mean(ms)), 1e3 * float(np.median(ms)), g.getStats()
 for fl in (True, False):
     mean, med, st = run(fl)
-    print(f"{w}x{h} {os.environ.get('MRH_LIB','default')[-20:]} frame={os.environ.get('MRH_FRAME','fused')} pref={os.environ.get('MRH_FUSED_PREF','-')} bulk={os.environ.get('MRH_BULK_DEPTH','-')} ctas={os.environ.get('MRH_FUSED_CTAS_PER_SM','-')} flushed={fl}: mean {mean:.1f} us median {med:.1f} us/frame  upd/frame {st['voxels_updated']/n:.0f} vis/frame {st['blocks_visible']/n:.0f}")
+    print(f"{w}x{h} {os.environ.get('MRH_LIB','default')[-20:]} frame={os.environ.get('MRH_FRAME','fused')} pref={os.environ.get('MRH_FUSED_PREF','-')} bulk={os.environ.get('MRH_BULK_DEPTH','-')} ctas={os.environ.get('MRH_FUSED_CTAS_PER_SM','-')} flushed={fl}: mean {mean:.1f} us median {med:.1f} us/frame  upd/frame {st['voxels_updated']/n:.0f} vis/frame {st['blocks_visible']/n:.0f} new/frame {st['blocks_new']/n:.1f}")
