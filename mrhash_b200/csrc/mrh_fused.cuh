@@ -35,6 +35,9 @@ namespace mrh {
 
 constexpr int kFuThreads = 128;
 constexpr int kFuWarps   = kFuThreads / 32;
+#ifndef MRH_BORDER_FIRST
+#define MRH_BORDER_FIRST 1 // tiles along the image border are claimed first (tile_of)
+#endif
 constexpr int kTileW     = 32; // one 128-byte depth row segment per bulk copy
 constexpr int kTileH     = 4;
 constexpr int kGcLocal   = 8; // condemned blocks a CTA removes itself on its way out; more go to the shared list
@@ -857,6 +860,7 @@ __device__ __forceinline__ void role_fuse(const MapDev& m, const FrameDev& f, co
 // ---------------------------------------------------------------------------------------------
 struct FusedPlan {
   uint32_t n_chunks, n_tiles, tiles_x;
+  uint32_t tiles_y; // tile rows of the whole image
   uint32_t prefer_fuse; // 1: this CTA looks at the fusion queue before the tile queue
   uint32_t shard;       // queue class of this CTA
 };
@@ -874,6 +878,7 @@ struct SchedState {
   uint32_t tile_a;     // the next tile of this CTA (assigned, or claimed two items ago)
   uint32_t tile_b;     // the one after it (claim in flight)
   uint32_t a_c0, a_r0; // pixel origin of tile_a
+  uint32_t a_tile;     // tile_a (a claim index) as a tile of the band
   uint32_t ticket;     // fusion-queue ticket assigned / claimed ahead of time, waiting for its entry
 };
 
@@ -887,11 +892,37 @@ __device__ __forceinline__ uint32_t claim(QueueWord* heads, uint32_t shard) {
   return shard + kQueueShards * (shard_base(shard) + atomicAdd(&heads[shard].v, 1u));
 }
 
+// Claim index -> tile of the band: the tiles along the image border first (left column, right column,
+// top row, bottom row), then the interior in image order. Whatever enters the view enters through the
+// border: those are the tiles whose rays find blocks missing and walk (10+ us each against 3 us for a
+// tile that stops at the patch test). Claimed in image order, a border tile of the lower half starts
+// when its CTA has finished two other tiles, and the end of the tile phase - hence the terminators,
+// hence the frame - waits for it.
+__device__ __forceinline__ uint32_t tile_of(const FusedPlan& plan, uint32_t i) {
+  const uint32_t tx = plan.tiles_x, ty = plan.tiles_y;
+  if (!MRH_BORDER_FIRST || tx < 3u || ty < 3u || plan.n_tiles != tx * ty || i >= plan.n_tiles)
+    return i;
+  if (i < ty)
+    return i * tx; // left column
+  i -= ty;
+  if (i < ty)
+    return i * tx + (tx - 1u); // right column
+  i -= ty;
+  if (i < tx - 2u)
+    return 1u + i; // top row
+  i -= tx - 2u;
+  if (i < tx - 2u)
+    return (ty - 1u) * tx + 1u + i; // bottom row
+  i -= tx - 2u;
+  return (1u + i / (tx - 2u)) * tx + 1u + i % (tx - 2u);
+}
+
 // depth rows of a tile -> shared memory (cp.async.bulk, one 128-byte row segment per copy); completes
 // on the buffer's mbarrier. `seq` = how many tiles this CTA has walked before this one: the buffer and
 // its barrier alternate, and buffer seq & 1 was last read two tiles ago.
 __device__ __forceinline__ void issue_depth(const FrameDev& f, const CameraDev& cam, const float* depth, const FusedPlan& plan, FusedSmem& sm, SchedState& st, uint32_t seq, int bulk_depth) {
-  const uint32_t tile = f.band_lo + st.tile_a;
+  st.a_tile           = tile_of(plan, st.tile_a);
+  const uint32_t tile = f.band_lo + st.a_tile;
   const uint32_t tx = tile % plan.tiles_x, ty = tile / plan.tiles_x;
   const uint32_t c0 = tx * kTileW, r0 = ty * kTileH;
   st.a_c0 = c0, st.a_r0 = r0, st.a_issued = true;
@@ -988,7 +1019,7 @@ __device__ __forceinline__ void schedule_next(const MapDev& m, const FrameDev& f
       if (st.tile_a < plan.n_tiles) {
         if (!st.a_issued)
           issue_depth(f, cam, depth, plan, sm, st, tile_seq, bulk_depth);
-        it.kind = kItemTile, it.arg = f.band_lo + st.tile_a;
+        it.kind = kItemTile, it.arg = f.band_lo + st.a_tile;
         it.pad[0] = st.a_c0, it.pad[1] = st.a_r0;
         st.tile_a = kNoTicket, st.a_issued = false;
         return;
@@ -1036,6 +1067,7 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
   plan.n_chunks    = (n_live + kFuThreads - 1) / kFuThreads;
   plan.n_tiles     = f.band_hi - f.band_lo;
   plan.tiles_x     = tiles_x;
+  plan.tiles_y     = (cam.rows + kTileH - 1) / kTileH;
   plan.prefer_fuse = ((blockIdx.x / num_sms) % pref_den) < pref_num ? 1u : 0u;
   plan.shard       = blockIdx.x % kQueueShards;
   if (tid == 0)
@@ -1047,7 +1079,7 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
   SchedState sched; // thread 0
   sched.chunk_open = true, sched.tile_open = true, sched.drained = false, sched.peeked = false;
   sched.next_chunk = blockIdx.x, sched.tile_a = blockIdx.x, sched.tile_b = kNoTicket, sched.ticket = kNoTicket;
-  sched.a_issued = false, sched.a_c0 = 0, sched.a_r0 = 0;
+  sched.a_issued = false, sched.a_c0 = 0, sched.a_r0 = 0, sched.a_tile = 0;
   if (tid == 0 && sched.tile_a < plan.n_tiles) // the first tile is assigned statically: its depth rows start moving now
     issue_depth(f, cam, depth, plan, sm, sched, 0, bulk_depth);
 
@@ -1068,10 +1100,18 @@ __global__ void __launch_bounds__(kFuThreads, MRH_FUSED_MIN_CTAS)
       t_a = gtimer();
       if (iter > 0) {
         const int pk = sm.item[(iter & 1u) ^ 1u].kind;
+#ifdef MRH_TRACE_LONG
+        // the long tile items of the frame: {tile, kind, item begin, item end (thread 0)}
+        if (pk == kItemTile && t_a - t_prev > 8000ull) {
+          const unsigned long long ti = atomicAdd(&m.ctr->dbg[30], 1ull);
+          if (ti < 8192) {
+            m.reint_keys[2 * ti]     = ((unsigned long long) sm.item[(iter & 1u) ^ 1u].arg << 32) | (unsigned) pk;
+#else
         if (blockIdx.x % 37 == 0) { // timeline of a sample of CTAs: {cta, kind, item begin, item end (thread 0)}
           const unsigned long long ti = atomicAdd(&m.ctr->dbg[30], 1ull);
           if (ti < 8192) {
             m.reint_keys[2 * ti]     = ((unsigned long long) blockIdx.x << 32) | (unsigned) pk;
+#endif
             m.reint_keys[2 * ti + 1] = ((t_prev & 0xFFFFFFFFull) << 32) | (t_a & 0xFFFFFFFFull);
           }
         }

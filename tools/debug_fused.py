@@ -36,7 +36,16 @@ for k in range(n):
             print(f"   {names[r]:5s}: items {v[8+r]:6d} sum {v[4+r]/1e3:9.1f} us  mean {v[4+r]/cnt/1e3:7.2f} us  last ended +{us(v[12+r]):.1f} us  longest {v[24+r]/1e3:.1f} us")
         print(f"   sched: sum {v[16]/1e3:.1f} us max {v[17]/1e3:.1f} us")
         print(f"   walked patches {v[29]}: ray off the fast path {v[18]}, box too large {v[19]}, block missing {v[28]}")
-    if k == n - 1:
+    if k >= n - 3 and os.environ.get('MRH_TRACE_LONG'):  # with a -DMRH_TRACE_LONG build: the tile items longer than 8 us
+        ntr = min(int(v[30]), 8192)
+        tb = (C.c_uint64 * (2 * max(ntr, 1)))()
+        lib.mrh_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]
+        lib.mrh_debug_trace(g._h, tb, 2 * ntr)
+        t0l = t0 & 0xFFFFFFFF
+        rows = sorted((int(tb[2 * i] >> 32), (((tb[2 * i + 1] >> 32) - t0l) & 0xFFFFFFFF) / 1e3, (((tb[2 * i + 1] & 0xFFFFFFFF) - t0l) & 0xFFFFFFFF) / 1e3) for i in range(ntr))
+        tiles_x = (w + 31) // 32
+        print(f'frame {k}: long tile items ((column,row) begin-end us): ' + ' '.join(f"({t % tiles_x},{t // tiles_x})[{a:.0f}-{b:.0f}]" for t, a, b in rows))
+    elif k == n - 1:
         ntr = min(int(v[30]), 8192)
         tb = (C.c_uint64 * (2 * ntr))()
         lib.mrh_debug_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t]
