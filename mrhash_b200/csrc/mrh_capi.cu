@@ -307,6 +307,8 @@ int mrh_params_default(mrh_params* p) {
   return 0;
 }
 
+static int init_map(mrh_map* m, const mrh_params* p, int dev);
+
 int mrh_create(const mrh_params* p, mrh_map** out) {
   if (!p || !out)
     return fail("null argument");
@@ -321,6 +323,17 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   mrh_map* m = new mrh_map();
   m->p       = *p;
   m->device  = dev;
+  // every failure below releases what has been built so far (free_map tolerates a half-built handle)
+  if (init_map(m, p, dev)) {
+    free_map(m);
+    delete m;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+static int init_map(mrh_map* m, const mrh_params* p, int dev) {
   CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&m->ev0));
   CK(cudaEventCreate(&m->ev1));
@@ -373,22 +386,15 @@ int mrh_create(const mrh_params* p, mrh_map** out) {
   m->hash_num_buckets  = nbuckets;
   m->max_num_triangles = ntri;
   m->max_stream_blocks = (uint64_t) (to_alloc * 0.10 / (12.0 * 512.0));
-  if (alloc_map(m)) {
-    free_map(m);
-    delete m;
+  if (alloc_map(m))
     return 1;
-  }
   // geowrapper.cpp:80: default 1x1 spherical camera
   static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
   memcpy(m->pose, I, sizeof(I));
   memcpy(m->cam_in_lidar, I, sizeof(I));
-  if (mrh_set_camera(m, 1.f, 1.f, 0.f, 0.f, 1, 1, p->min_depth, p->max_depth, 1) || reset_map(m)) {
-    free_map(m);
-    delete m;
+  if (mrh_set_camera(m, 1.f, 1.f, 0.f, 0.f, 1, 1, p->min_depth, p->max_depth, 1) || reset_map(m))
     return 1;
-  }
   CK(cudaStreamSynchronize(m->stream));
-  *out = m;
   return 0;
 }
 
