@@ -488,6 +488,10 @@ def main():
     for k in range(W):
         step_host(k)
     barrier()
+    if scatter and W > 0:
+        # the band upload + all-gather must have delivered the whole frame to every rank (checked once, untimed)
+        kb = (e2e_state["n"] - 1) & 1
+        assert torch.equal(bcast_d[kb].cpu(), depth_h[W - 1]) and torch.equal(bcast_c[kb].cpu(), rgb_h[W - 1]), "scatter ingest delivered a different frame"
     host_us = {k: 0.0 for k in host_us}
     windows.append([time.time(), None])
     prof_range(True)

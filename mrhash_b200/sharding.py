@@ -54,6 +54,9 @@ def broadcast_frame(depth, rgb, pose, src=0, group=None):
     dist.broadcast(rgb, src, group=group)
 
 
+_COALESCED_GATHER = [True]  # cleared on the first failure of the grouped NCCL all-gather
+
+
 def frame_row_band(rank, world, rows):
     """Rows [lo, hi) of a frame that `rank` uploads in scatter_ingest_frame (equal bands; rows % world == 0)."""
     band = rows // world
@@ -97,7 +100,18 @@ def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None, v
     lo, hi = v["lo"], v["hi"]
     v["d_band"].copy_(depth_host[lo:hi], non_blocking=True)
     v["c_band"].copy_(rgb_host[lo:hi], non_blocking=True)
-    # in place: each rank's input is its own band of the output (NCCL's in-place all-gather layout)
+    # in place: each rank's input is its own band of the output (NCCL's in-place all-gather layout).
+    # On NCCL both images go in ONE grouped launch (the per-collective host cost of torch.distributed is
+    # what bounds a 8-rank step); elsewhere (gloo in the CPU tests) as two collectives.
+    if depth_dev.is_cuda and _COALESCED_GATHER[0]:
+        try:
+            pg = group if group is not None else dist.distributed_c10d._get_default_group()
+            work = pg.allgather_into_tensor_coalesced([v["d_all"], v["c_all"]], [v["d_in"], v["c_in"]])
+            if work is not None:
+                work.wait()  # stream-ordered on NCCL: the current stream waits, the host does not
+            return
+        except (AttributeError, RuntimeError, TypeError):
+            _COALESCED_GATHER[0] = False  # this torch / backend has no coalesced all-gather: two calls from now on
     dist.all_gather_into_tensor(v["d_all"], v["d_in"], group=group)
     dist.all_gather_into_tensor(v["c_all"], v["c_in"], group=group)
 
