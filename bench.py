@@ -423,6 +423,11 @@ def main():
     bcast_c = [b[4 * P :].view(args.height, args.width, 3) for b in bcast] if world > 1 else None
     scatter = world > 1 and args.height % world == 0 and os.environ.get("MRH_BENCH_INGEST", "scatter") != "broadcast"
     scatter_views = [sharding.scatter_views(bcast_d[b], bcast_c[b]) for b in range(2)] if scatter else None
+    if scatter:  # this rank's band of every host frame, sliced once
+        lo_r, hi_r = sharding.frame_row_band(rank, world, args.height)
+        band_d = [depth_h[k][lo_r:hi_r] for k in range(n)]
+        band_c = [rgb_h[k][lo_r:hi_r] for k in range(n)]
+    torch_stream = torch.cuda.current_stream()
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
     for e in ev_done:
@@ -465,11 +470,11 @@ def main():
         # (and the broadcast that reuses this buffer, two frames on, after this frame's kernels).
         b = e2e_state["n"] & 1
         g.setCurrPose(*poses[k])
-        torch.cuda.current_stream().wait_event(ev_done[b])
+        torch_stream.wait_event(ev_done[b])
         if scatter:
             # every rank uploads its band of rows over its own PCIe link; an in-place all-gather over
             # NVLink completes the frame everywhere (sharding.scatter_ingest_frame)
-            sharding.scatter_ingest_frame(bcast_d[b], bcast_c[b], depth_h[k], rgb_h[k], views=scatter_views[b])
+            sharding.scatter_ingest_frame(bcast_d[b], bcast_c[b], band_d[k], band_c[k], views=scatter_views[b])
         else:
             if rank == 0:
                 bcast_d[b].copy_(depth_h[k], non_blocking=True)

@@ -98,8 +98,9 @@ def scatter_ingest_frame(depth_dev, rgb_dev, depth_host, rgb_host, group=None, v
         return
     v = views if views is not None else scatter_views(depth_dev, rgb_dev, group)
     lo, hi = v["lo"], v["hi"]
-    v["d_band"].copy_(depth_host[lo:hi], non_blocking=True)
-    v["c_band"].copy_(rgb_host[lo:hi], non_blocking=True)
+    # (a caller that slices its host frames once hands over the band itself: [hi - lo, W] instead of [H, W])
+    v["d_band"].copy_(depth_host if depth_host.shape[0] == hi - lo else depth_host[lo:hi], non_blocking=True)
+    v["c_band"].copy_(rgb_host if rgb_host.shape[0] == hi - lo else rgb_host[lo:hi], non_blocking=True)
     # in place: each rank's input is its own band of the output (NCCL's in-place all-gather layout).
     # On NCCL both images go in ONE grouped launch (the per-collective host cost of torch.distributed is
     # what bounds a 8-rank step); elsewhere (gloo in the CPU tests) as two collectives.
