@@ -12,21 +12,26 @@
 //   chunk  128 entries of the input live list: frustum test (isSDFBlockInCameraFrustumApprox),
 //          live-list compaction, visible list; blocks that can receive depth this frame are
 //          appended to the fusion queue fq[];
-//   tile   32 x 4 depth pixels: the depth rows arrive in shared memory through cp.async.bulk on an
-//          mbarrier; each warp walks the block DDA of an 8 x 4 pixel patch; visited keys are
-//          de-duplicated in a per-CTA shared-memory set and each distinct key is resolved once by a
-//          warp-cooperative find-or-insert on the 128-byte bucket rows; a new block goes straight to
-//          the output live list, the visible list and fq[];
+//   tile   32 x 4 depth pixels (border tiles of the image are claimed first, tile_of): the depth rows
+//          arrive in shared memory through cp.async.bulk on an mbarrier; each warp owns an 8 x 4 pixel
+//          patch and first tests whether any of its rays can reach a block that does not exist (the
+//          union box of the ray-end blocks, one lane per block) - nearly always not, and the patch is
+//          done; otherwise it walks the block DDA; visited keys are de-duplicated in a per-CTA
+//          shared-memory set and each distinct missing key is resolved once by a warp-cooperative
+//          find-or-insert on the 128-byte bucket rows; a new block goes straight to the output live
+//          list, the visible list and fq[];
 //   fuse   one entry of fq[]: the block's three planes (6 KB, contiguous) are pulled into shared
 //          memory by ONE cp.async.bulk issued before the projection pass and awaited on an mbarrier
 //          after it; 4 consecutive-x voxels per thread, 128-bit shared loads and global stores.
 // Blocks that already existed do not depend on the ray walk, so fusion of the visible list overlaps
-// it; blocks inserted by the walk are fused as they appear. Removing a block (GC) is deferred to the
-// finaliser (the last CTA to finish): during the frame no key ever leaves the table, so a walker can
-// never re-insert a block that the reference would still have seen (its GC runs after allocation),
-// and the free stack receives the freed blocks after every allocation of the frame, as in the reference.
-// No CTA ever waits for a specific other CTA: items are claimed dynamically, and a CTA that finds
-// nothing to do polls the producer-completion counters.
+// it; blocks inserted by the walk are fused as they appear. Removing a block (GC) is deferred until
+// every walk of the frame is over: a CTA removes the blocks it condemned on its way out (it leaves only
+// after seeing a terminator, and those are written after the last tile), so a walker can never
+// re-insert a block that the reference would still have seen (its GC runs after allocation), and the
+// free stack receives the freed blocks after every allocation of the frame, as in the reference.
+// No CTA ever waits for a specific other CTA and nobody polls a shared word: items are claimed with
+// blind fetch-and-add tickets, and a CTA with nothing to do polls the 32-byte queue entry its own
+// ticket names until a block or a terminator appears there.
 #pragma once
 #include "mrh_div.cuh"
 #include "mrh_kernels.cuh"
