@@ -20,12 +20,15 @@ block allocation -> visibility -> TSDF fusion + garbage collection (one persiste
 `--impl reference` runs the UNMODIFIED reference kernels (oracle/_ref/libref_harness.so, compiled
 from /root/reference for sm_100a) on the same stream, host buffers in, the way GeoWrapper::compute
 drives them: `value` is the CUDA-event time of its integrate() section (device time, like ours),
-`e2e` its wall-clock frames/s with host buffers. N>1 (torchrun): the map is sharded by hash-bucket
-range, rank 0 ingests each frame and broadcasts it over NCCL; every rank allocates / fuses only the
-blocks it owns (starve frames min-reduce the z-buffer over the ranks). Two more keys at N>1:
-`replica_streams` (one unsharded stream per GPU, no collective) and `sharded_mesh` (boundary exchange
-+ marching cubes in place + soup gather + weld, timed). stdout carries exactly one JSON line;
-everything else goes to stderr.
+`e2e` its wall-clock frames/s with host buffers. N>1 (torchrun): the workload is BASELINE configs[3]
+(1280x960, 2000-frame orbit - NOT the 640x480 stream of `--gpus 1`); the map is sharded by hash-bucket
+range, every rank uploads its band of rows of each frame and an NCCL all-gather completes it
+(sharding.scatter_ingest_frame); every rank allocates / fuses only the blocks it owns (starve frames
+min-reduce the z-buffer over the ranks). More keys at N>1: `replica_streams` (one unsharded stream per
+GPU, no collective), `single_gpu_same_workload` (what one GPU does on this line's stream: the
+denominator for a scaling figure on this workload) and `sharded_mesh` (boundary exchange + marching
+cubes in place + soup gather + weld, timed). stdout carries exactly one JSON line; everything else
+goes to stderr.
 """
 import argparse
 import json
@@ -567,7 +570,11 @@ def main():
         barrier()
         ms_rep = max_over_ranks(r0.elapsed_time(r1))
         g.close()
-        extra_multi["replica_streams"] = {"value": world * K / (ms_rep * 1e-3), "unit": "frames/s", "scaling": "weak", "what": "one unsharded stream per GPU, L2 warm, aggregate over ranks"}
+        extra_multi["replica_streams"] = {"value": world * K / (ms_rep * 1e-3), "unit": "frames/s", "scaling": "weak", "what": "one unsharded stream per GPU, L2 warm, aggregate over ranks",
+                                          "per_gpu": K / (ms_rep * 1e-3)}
+        # `bench.py --gpus 1` runs configs[1] (640x480); what ONE GPU does on THIS line's workload is the
+        # per-GPU figure above (an unsharded map of the same stream), to be compared with stream_fps_l2_warm
+        extra_multi["single_gpu_same_workload"] = {"value": K / (ms_rep * 1e-3), "unit": "frames/s", "what": "one GPU, unsharded map, the same 1280x960 stream, L2 as the stream leaves it (compare: stream_fps_l2_warm of this line)"}
         # (ii) meshing the sharded map of the e2e pass where it lies: boundary exchange (two NCCL
         # all-to-alls), marching cubes per rank, soup gather + weld on rank 0
         barrier()
