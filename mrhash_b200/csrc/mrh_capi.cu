@@ -250,12 +250,18 @@ static int ingest_upload(mrh_map* m, Ingest& in, const T* src_or_null, size_t n,
     direct = cudaPointerGetAttributes(&attr, src_or_null) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
   }
+  const int tl_lane = &in == &m->in_rgb ? 1 : 0;
+  mrh_map::TimelineFrame* tl = (&in == &m->in_depth || &in == &m->in_rgb) && m->timeline_up_next[tl_lane] < m->timeline.size() ? &m->timeline[m->timeline_up_next[tl_lane]++] : nullptr;
   if (direct) {
     // mode 2: this device image was filled two setter calls ago; that transfer read a caller buffer
     // which the caller may reuse from now on (the contract of mrh_set_ingest_mode)
     if (m->ingest_mode == 2)
       CK(cudaEventSynchronize(in.copied[w]));
+    if (tl)
+      CK(cudaEventRecord(tl->up0[tl_lane], in.stream));
     CK(cudaMemcpyAsync(in.d_buf[w], src_or_null, bytes, cudaMemcpyHostToDevice, in.stream));
+    if (tl)
+      CK(cudaEventRecord(tl->up1[tl_lane], in.stream));
     CK(cudaEventRecord(in.copied[w], in.stream));
     in.pending_direct = true;
   } else {
@@ -623,8 +629,16 @@ static int compute_frame(mrh_map* m) {
         CK(cudaStreamWaitEvent(m->stream, in->copied[in->which], 0));
     }
   CK(cudaEventRecord(m->ev0, m->stream));
+  mrh_map::TimelineFrame* tl = rgbd && m->timeline_next < m->timeline.size() ? &m->timeline[m->timeline_next++] : nullptr;
+  if (tl) {
+    if (m->rgb_ready) // (the fused frame waits for the colour in front of its launch: make the stamp see it too)
+      CK(cudaStreamWaitEvent(m->stream, m->rgb_ready, 0));
+    CK(cudaEventRecord(tl->k0, m->stream));
+  }
   if (rgbd && integrate_rgbd(m))
     return 1;
+  if (tl)
+    CK(cudaEventRecord(tl->k1, m->stream));
   if (m->n_points && integrate_points(m))
     return 1;
   CK(cudaEventRecord(m->ev1, m->stream));
@@ -645,6 +659,44 @@ static int compute_frame(mrh_map* m) {
     m->ctr_filled              = std::min(m->ctr_filled + 1, (int) mrh_map::kCtrRing);
   }
   return 0;
+}
+
+/* tuning: device-side timeline of the streaming path. mrh_debug_timeline(m, n, nullptr) arms timing events for
+ * the next n RGB-D frames; mrh_debug_timeline(m, 0, out) waits and writes 6 floats per frame (microseconds
+ * since the first stamp): depth upload begin / end, colour upload begin / end, frame kernel begin / end */
+extern "C" int mrh_debug_timeline(mrh_map* m, int arm_frames, float* out) {
+  GUARD(m);
+  if (arm_frames > 0) {
+    m->timeline.resize((size_t) arm_frames);
+    for (auto& t : m->timeline) {
+      for (int k = 0; k < 2; ++k) {
+        CK(cudaEventCreate(&t.up0[k]));
+        CK(cudaEventCreate(&t.up1[k]));
+      }
+      CK(cudaEventCreate(&t.k0));
+      CK(cudaEventCreate(&t.k1));
+    }
+    m->timeline_next = m->timeline_up_next[0] = m->timeline_up_next[1] = 0;
+    return 0;
+  }
+  CK(cudaDeviceSynchronize());
+  const size_t n = std::min(m->timeline_next, std::min(m->timeline_up_next[0], m->timeline_up_next[1]));
+  for (size_t i = 0; i < n && out; ++i) {
+    const auto& t = m->timeline[i];
+    cudaEvent_t ev[6] = {t.up0[0], t.up1[0], t.up0[1], t.up1[1], t.k0, t.k1};
+    for (int k = 0; k < 6; ++k) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, m->timeline[0].up0[0], ev[k]));
+      out[6 * i + k] = ms * 1e3f;
+    }
+  }
+  for (auto& t : m->timeline) {
+    for (int k = 0; k < 2; ++k)
+      cudaEventDestroy(t.up0[k]), cudaEventDestroy(t.up1[k]);
+    cudaEventDestroy(t.k0), cudaEventDestroy(t.k1);
+  }
+  m->timeline.clear();
+  return (int) n;
 }
 
 /* tuning builds (-DMRH_FUSED_DEBUG): reads the 32 timer words of the fused kernel and re-arms them */

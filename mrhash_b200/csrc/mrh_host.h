@@ -99,6 +99,13 @@ struct mrh_map {
 
   // ingest: copies run on their own stream into double-buffered device images, so the transfer of
   // frame k+1 overlaps the kernels of frame k (mrh_capi.cu: struct use in ingest_upload)
+  // MRH_TIMELINE=n (tuning): timing events around the uploads and the frame of the first n frames after
+  // the switch, printed by mrh_debug_timeline (device-side timeline of the streaming path)
+  struct TimelineFrame {
+    cudaEvent_t up0[2]{}, up1[2]{}, k0 = nullptr, k1 = nullptr;
+  };
+  std::vector<TimelineFrame> timeline;
+  size_t timeline_next = 0, timeline_up_next[2] = {0, 0};
   cudaStream_t copy_stream = nullptr;  // H2D of depth images / points
   cudaStream_t copy_stream2 = nullptr; // H2D of colour images / normals: the two uploads of a frame overlap their fixed costs
   mrh::Ingest in_depth, in_rgb, in_points, in_normals;
