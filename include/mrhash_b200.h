@@ -216,8 +216,8 @@ int mrh_get_field(mrh_map* m, const char* name, double* out);
 int mrh_set_field(mrh_map* m, const char* name, double value);
 
 int mrh_get_stats(mrh_map* m, mrh_stats* out);
-/* Statistics without a stall per frame: once enabled, every mrh_compute() is followed by an asynchronous
- * copy of the counters into one of four page-locked slots; mrh_get_stats_pipelined(which = k) returns
+/* Statistics without a stall per frame: once enabled, every mrh_compute() ends with a one-CTA kernel that
+ * writes the counters into one of four page-locked (mapped) slots; mrh_get_stats_pipelined(which = k) returns
  * the state after the frame k compute() calls before the last one (k = 0 .. 3; it waits for that frame
  * only). A caller that reads which = 2 after every compute() sees every frame's result two frames late
  * and never waits for a kernel it has just queued, so the next frame's upload is submitted while the

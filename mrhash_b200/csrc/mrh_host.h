@@ -141,8 +141,8 @@ struct mrh_map {
   // (the setter copies, reference semantics), 1 = DMA from the caller's buffer, awaited at the end of
   // compute(), 2 = DMA from the caller's buffer, never awaited by compute() (streaming callers)
   int ingest_mode = 0;
-  // pipelined statistics (mrh_set_stats_pipeline): every compute() is followed by an asynchronous copy
-  // of the counters into one of two pinned slots; mrh_get_stats_pipelined returns the previous frame's
+  // pipelined statistics (mrh_set_stats_pipeline): every compute() ends with k_snapshot_counters writing
+  // the counters into one of kCtrRing pinned (mapped) slots; mrh_get_stats_pipelined reads an earlier frame's
   static constexpr int kCtrRing = 4;
   mrh::Counters* h_ctr_ring = nullptr; // kCtrRing pinned slots
   cudaEvent_t ev_ctr[kCtrRing]{};
