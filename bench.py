@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
-STATS_LAG = 2  # e2e passes read every frame's counters this many frames after submitting it
+STATS_LAG = int(os.environ.get("MRH_BENCH_STATS_LAG", "2"))  # e2e passes read every frame's counters this many frames after submitting it
 COUNTERS_BYTES = 144  # the part of mrh::Counters that getStats() / mrh_get_stats_pipelined read back
 
 
