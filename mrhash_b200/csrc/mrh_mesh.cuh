@@ -16,6 +16,9 @@
 // mrh_math.cuh); the contraction pattern of the trilinear polynomial and of vertexInterp was read
 // from the SASS of the reference objects.
 #pragma once
+#ifndef MRH_MC_TIGHT
+#define MRH_MC_TIGHT 1 // second, tighter pre-filter of k_mc_blocks (corner means)
+#endif
 #include "mrh_mc_tables.cuh"
 #include "mrh_table.cuh"
 
@@ -317,30 +320,62 @@ __device__ __forceinline__ void mc_emit(const CellResult& c, float* tri_out /* n
 //    abandoned.
 // In each case the full evaluation would emit nothing, so skipping it changes no output bit. Most
 // voxels of a TSDF band are on one side of the surface with their whole neighbourhood.
-__device__ __forceinline__ bool halo_cell_is_empty(const float* s_sdf, const uint32_t* s_cw, int vi) {
+//
+// Second, tighter test when all 27 voxels are observed. Every corner is then valid, and its value is the
+// trilinear blend of its 2 x 2 x 2 voxels with weights (1/2 +- a)(1/2 +- b)(1/2 +- c): the blend
+// fraction is RN((pos - dual) / w) with pos - dual = vs / 2 up to the rounding of `dual` and w = vs up
+// to the rounding of `dual + vs` (both subtractions are exact, Sterbenz), so |a|, |b|, |c| <= delta =
+// 2.1 k u, k = the largest voxel coordinate involved, u = 2^-24. Hence |corner - mean of the 8 voxels|
+// <= ((1 + 2 delta)^3 - 1) max|sdf| <= 6.2 delta max|sdf| (+ 3e-5 max|sdf| of evaluation rounding).
+// `slack` = 6.2 * (twice that delta) + 1e-4, computed once per block from its coordinates: if the eight
+// means all exceed slack * max|sdf|, or are all below its negative, the eight corners share that sign
+// and the cell has no triangle. This removes the cells one to two voxels away from the surface, which
+// pass the neighbourhood sign test but cannot be crossed.
+__device__ __forceinline__ bool halo_cell_is_empty(const float* s_sdf, const uint32_t* s_cw, int vi, float slack) {
   const int x = vi & 7, y = (vi >> 3) & 7, z = vi >> 6; // halo cell (x + 1, y + 1, z + 1)
   float lo = 3.4e38f, hi = -3.4e38f;
   uint32_t w = 0;
-  bool finite = true;
+  bool finite = true, all_seen = true;
+  float v[27];
 #pragma unroll
   for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int c   = ((z + dz) * 10 + (y + dy)) * 10 + (x + dx);
+        const int c       = ((z + dz) * 10 + (y + dy)) * 10 + (x + dx);
         const uint32_t wc = s_cw[c] >> 24;
+        const float sv    = s_sdf[c];
+        v[(dz * 3 + dy) * 3 + dx] = sv;
         if (wc) { // unobserved voxels never supply a value (see above)
-          const float v = s_sdf[c];
-          lo = fminf(lo, v), hi = fmaxf(hi, v);
-          finite &= fabsf(v) < 1e30f; // false for NaN too (fminf / fmaxf would drop it silently)
+          lo = fminf(lo, sv), hi = fmaxf(hi, sv);
+          finite &= fabsf(sv) < 1e30f; // false for NaN too (fminf / fmaxf would drop it silently)
+        } else {
+          all_seen = false;
         }
         w |= wc;
       }
   if (!finite)
     return false; // NaN / Inf / absurd payloads: let the full path decide
-  const float margin = 1e-4f * fmaxf(fabsf(lo), fabsf(hi));
-  return w == 0u || lo > margin || hi < -margin;
+  const float big    = fmaxf(fabsf(lo), fabsf(hi));
+  const float margin = 1e-4f * big;
+  if (w == 0u || lo > margin || hi < -margin)
+    return true;
+  if (!MRH_MC_TIGHT || !all_seen)
+    return false;
+  float cmin = 3.4e38f, cmax = -3.4e38f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ox = k & 1, oy = (k >> 1) & 1, oz = k >> 2;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sum += v[((oz + (j >> 2)) * 3 + oy + ((j >> 1) & 1)) * 3 + ox + (j & 1)];
+    const float mean = 0.125f * sum;
+    cmin = fminf(cmin, mean), cmax = fmaxf(cmax, mean);
+  }
+  const float m2 = slack * big;
+  return cmin > m2 || cmax < -m2;
 }
 
 // One CTA of kMcThreads per live block. Small CTAs: per block the kernel is a chain of dependent
@@ -394,6 +429,8 @@ __global__ void __launch_bounds__(kMcThreads, 1024 / kMcThreads) k_mc_blocks(Map
     const bool generic = s_mixed != 0;
     // the pre-filter's bounds assume voxel coordinates far below 2^23 (positions exact to vs / 16)
     const bool prefilter = m.min_weight_threshold > 0 && max(max(abs(b.x), abs(b.y)), abs(b.z)) < (1 << 16);
+    // blend-fraction bound of the tighter test: delta = 2.1 k u, doubled, k = largest voxel coordinate around the block
+    const float slack = 6.2f * (4.2f * (float) (8 * (max(max(abs(b.x), abs(b.y)), abs(b.z)) + 2)) * 5.9604645e-8f) + 1e-4f;
     if (!generic) {
       for (int c = tid; c < 1000; c += kMcThreads) {
         const int i = c % 10, j = (c / 10) % 10, k = c / 100;
@@ -417,7 +454,7 @@ __global__ void __launch_bounds__(kMcThreads, 1024 / kMcThreads) k_mc_blocks(Map
     int n_vox = res ? 64 : 512;
     if (!generic && prefilter) {
       for (int vi = tid; vi < 512; vi += kMcThreads) {
-        const bool keep      = !halo_cell_is_empty(s_sdf, s_cw, vi);
+        const bool keep      = !halo_cell_is_empty(s_sdf, s_cw, vi, slack);
         const unsigned votes = __ballot_sync(0xFFFFFFFFu, keep);
         uint32_t base        = 0;
         if (lane == 0 && votes)
