@@ -46,6 +46,7 @@ sys.path.insert(0, ROOT)
 NUM_SDF_BLOCKS = 500000  # the reference's own test sizing (tests/test_hash_utils.cu:175-190)
 HASH_NUM_BUCKETS = 250000
 L2_FLUSH_BYTES = 256 << 20
+ALL_CPUS = os.sched_getaffinity(0)  # before bind_near_gpu narrows it
 STATS_LAG = int(os.environ.get("MRH_BENCH_STATS_LAG", "2"))  # e2e passes read every frame's counters this many frames after submitting it
 COUNTERS_BYTES = 144  # the part of mrh::Counters that getStats() / mrh_get_stats_pipelined read back
 
@@ -182,6 +183,8 @@ def cpu_baseline(args, depth_h, rgb_h, poses, budget_s):
 
     from mrhash_b200 import synth
 
+    bound = os.sched_getaffinity(0)
+    os.sched_setaffinity(0, ALL_CPUS)  # the CPU arm gets every core of the box, not only the GPU's NUMA node
     cores = len(os.sched_getaffinity(0))
     p = dict(synth.REPLICA_PARAMS)
     o = Oracle(p, 100000, 50000, threads=cores)
@@ -194,6 +197,7 @@ def cpu_baseline(args, depth_h, rgb_h, poses, budget_s):
         o.compute_rgbd(synth.quat_to_matrix_f32(t, q), depth_h[n], rgb_h[n])
         n += 1
     dt = time.perf_counter() - t0
+    os.sched_setaffinity(0, bound)
     return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"first {n} frames of the same {args.width}x{args.height} stream ({dt:.1f} s), oracle/mrh_oracle.c with OpenMP over pixel rows / blocks"}
 
 
@@ -269,6 +273,48 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(gpu_index):
+    """Run this process on the CPUs of the GPU's NUMA node, so that the page-locked frames it allocates (first
+    touch) sit behind the PCIe root the GPU hangs on: the same 1.2 MB upload was measured at 47 GB/s from the
+    near node and 20-31 GB/s from the far one. Returns what was done, for the JSON line. MRH_BENCH_NUMA=0 skips it."""
+    if os.environ.get("MRH_BENCH_NUMA", "1") == "0":
+        return "not bound (MRH_BENCH_NUMA=0)"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "not bound (the device reports no NUMA node)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        done = []
+        # memory first: prefer the node for every later allocation of this process (MPOL_PREFERRED), whether or
+        # not its CPUs are ours to run on
+        try:
+            import ctypes
+
+            mask = ctypes.c_ulong(1 << node)
+            if ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 8 * ctypes.sizeof(mask)) == 0:  # set_mempolicy
+                done.append(f"memory preferred on NUMA node {node}")
+        except Exception:
+            pass
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            done.append(f"{len(cpus)} CPUs of NUMA node {node}")
+        return (", ".join(done) + f" (GPU {gpu_index})") if done else f"not bound (node {node}: no usable CPU, no memory policy)"
+    except Exception as exc:  # no NVML / no sysfs: run wherever the scheduler put us
+        return f"not bound ({type(exc).__name__})"
+
+
 def main():
     # stdout carries exactly one JSON line: everything else that writes to fd 1 (the library's
     # reference-style progress prints, NCCL's version banner) goes to stderr
@@ -280,6 +326,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_near_gpu(local)  # both arms, before anything allocates host memory
+    print(f"[bench] host placement: {numa}", file=sys.stderr, flush=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -690,6 +738,7 @@ def main():
                 "num_sdf_blocks": NUM_SDF_BLOCKS,
                 "hash_num_buckets": HASH_NUM_BUCKETS,
                 "l2": "flushed before every step (256 MiB memset, excluded from the per-step CUDA-event window)",
+                "host_placement": numa,
                 "parallelism": "1 GPU" if world == 1 else f"map sharded by hash-bucket range over {world} GPUs; e2e: frame " + ("uploaded in row bands by all ranks + NCCL all-gather" if scatter else "uploaded by rank 0 + NCCL broadcast"),
             },
             "mvoxels_updated_per_sec": v_upd / (ms_flushed * 1e-3) / 1e6,
