@@ -459,10 +459,14 @@ def main():
     g.close()
 
     # ---------------- pass B: end to end through the public API, host buffers ----------------------
-    depth_h = torch.empty(depth.shape, dtype=depth.dtype, pin_memory=True)
-    rgb_h = torch.empty(rgb.shape, dtype=rgb.dtype, pin_memory=True)
-    depth_h.copy_(depth)
-    rgb_h.copy_(rgb)
+    # N > 1 (8.6 MB frames, one copy of the stream per rank): the end-to-end pass runs at most 400 timed
+    # steps, so that eight ranks do not page-lock 70 GB of host memory between them
+    Ke = K if world == 1 else min(K, 400)
+    ne = W + Ke
+    depth_h = torch.empty((ne,) + tuple(depth.shape[1:]), dtype=depth.dtype, pin_memory=True)
+    rgb_h = torch.empty((ne,) + tuple(rgb.shape[1:]), dtype=rgb.dtype, pin_memory=True)
+    depth_h.copy_(depth[:ne])
+    rgb_h.copy_(rgb[:ne])
     depth_np, rgb_np = depth_h.numpy(), rgb_h.numpy()
     g = new_map(args, rank, world, local, max_num_triangles=4_000_000 if world > 1 else 1)
     stream = torch.cuda.ExternalStream(g.cudaStream(), device=dev)
@@ -476,8 +480,8 @@ def main():
     scatter_views = [sharding.scatter_views(bcast_d[b], bcast_c[b]) for b in range(2)] if scatter else None
     if scatter:  # this rank's band of every host frame, sliced once
         lo_r, hi_r = sharding.frame_row_band(rank, world, args.height)
-        band_d = [depth_h[k][lo_r:hi_r] for k in range(n)]
-        band_c = [rgb_h[k][lo_r:hi_r] for k in range(n)]
+        band_d = [depth_h[k][lo_r:hi_r] for k in range(ne)]
+        band_c = [rgb_h[k][lo_r:hi_r] for k in range(ne)]
     torch_stream = torch.cuda.current_stream()
     ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -554,11 +558,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
-    for i in range(K):
+    for i in range(Ke):
         step_host(W + i)
     for lag in range(STATS_LAG - 1, -1, -1):  # the results of the last steps (waits for those frames only)
         last_stats = g.getStatsPipelined(lag)
-    assert last_stats["frames"] >= K, last_stats
+    assert last_stats["frames"] >= Ke, last_stats
     e1.record(stream)
     g.synchronize()
     barrier()
@@ -748,7 +752,7 @@ def main():
             "live_blocks_end": live,
             "stream_fps_l2_warm": K / (ms_stream * 1e-3),
             "value_kind": "device time: CUDA events around each compute(), device-resident inputs, L2 flushed before every step",
-            "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / K, "host_us_per_step": {k: 1e6 * v / K for k, v in host_us.items()},
+            "e2e": {"value": Ke / (ms_e2e * 1e-3), "unit": "frames/s", "steps": Ke, "h2d_bytes_per_step": P * 7, "d2h_bytes_per_step": COUNTERS_BYTES, "ms_per_step": ms_e2e / Ke, "host_us_per_step": {k: 1e6 * v / Ke for k, v in host_us.items()},
                     "what": "page-locked host frames in (mrh_set_ingest_mode 2: DMA overlaps the previous frame's kernel), counters of every frame read back two frames late (mrh_get_stats_pipelined)" if world == 1 else ("every rank uploads its band of rows from page-locked host memory over its own PCIe link, in-place NCCL all-gather over NVLink completes the frame on every rank (sharding.scatter_ingest_frame), alternating buffers" if scatter else "rank 0 ingests from page-locked host frames, one NCCL broadcast per frame into alternating buffers") + " (overlaps the previous frame's kernels), counters of every frame read back two frames late"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo[dom], "ms_per_launch": per_kernel[dom]["ms_per_launch"]},
