@@ -201,7 +201,7 @@ def cpu_baseline(args, depth_h, rgb_h, poses, budget_s):
     return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"first {n} frames of the same {args.width}x{args.height} stream ({dt:.1f} s), oracle/mrh_oracle.c with OpenMP over pixel rows / blocks"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, numa=""):
     """The reference's own kernels (oracle/_ref), driven like GeoWrapper::compute, host buffers in."""
     if rank != 0:
         return
@@ -261,7 +261,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload(args), "num_sdf_blocks": NUM_SDF_BLOCKS, "hash_num_buckets": HASH_NUM_BUCKETS, "l2": "not flushed (host-driven, synchronous reference)", "parallelism": "1 GPU (the reference has no multi-GPU path)"},
+        "config": {"workload": workload(args), "num_sdf_blocks": NUM_SDF_BLOCKS, "hash_num_buckets": HASH_NUM_BUCKETS, "l2": "not flushed (host-driven, synchronous reference)", "host_placement": numa, "parallelism": "1 GPU (the reference has no multi-GPU path)"},
         "integrate_only_fps": fps_dev,
         "wall_clock_fps": fps_wall,
         "visible_blocks_last_frame": occupied,
@@ -329,7 +329,7 @@ def main():
     numa = bind_near_gpu(local)  # both arms, before anything allocates host memory
     print(f"[bench] host placement: {numa}", file=sys.stderr, flush=True)
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, numa)
         return
 
     import torch
