@@ -25,6 +25,18 @@ using namespace mrh;
 
 namespace mrh {
 
+// device staging buffer released on every return path (the CK macro returns from the caller)
+template <typename T>
+struct ScopedDev {
+  T* p = nullptr;
+  ~ScopedDev() {
+    cudaFree(p);
+  }
+  cudaError_t alloc(size_t count) {
+    return cudaMalloc(&p, sizeof(T) * (count ? count : 1));
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // k_gather_blocks: live list -> dense (record, AoS payload) buffers for streamAllOut /
 // serializeData / the parity dump (replaces the Streamer's integrateFromGlobalHashPass1/2,
@@ -237,12 +249,14 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
       return 0;
     // bounded staging so that a 100 GB map does not need a 100 GB mirror on the device
     const size_t chunk = std::min<size_t>(n, 1u << 16);
-    GatherRecord* d_recs = nullptr;
-    uint32_t* d_vox      = nullptr;
-    uint32_t* d_count    = nullptr;
-    CK(cudaMalloc(&d_recs, sizeof(GatherRecord) * chunk));
-    CK(cudaMalloc(&d_vox, sizeof(uint32_t) * 3 * kBlockVoxels * chunk));
-    CK(cudaMalloc(&d_count, sizeof(uint32_t)));
+    ScopedDev<GatherRecord> recs_buf;
+    ScopedDev<uint32_t> vox_buf, count_buf; // released on every return path
+    CK(recs_buf.alloc(chunk));
+    CK(vox_buf.alloc((size_t) 3 * kBlockVoxels * chunk));
+    CK(count_buf.alloc(1));
+    GatherRecord* d_recs = recs_buf.p;
+    uint32_t* d_vox      = vox_buf.p;
+    uint32_t* d_count    = count_buf.p;
     const size_t base = recs.size();
     recs.resize(base + n);
     voxels.resize((base + n) * 3 * kBlockVoxels);
@@ -264,7 +278,6 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
         return 1;
       done += got;
     }
-    cudaFree(d_recs), cudaFree(d_vox), cudaFree(d_count);
     recs.resize(base + done);
     voxels.resize((base + done) * 3 * kBlockVoxels);
     return 0;
@@ -333,10 +346,12 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
   // one pass: records with pairwise different keys
   static int insert_pass(mrh_map* m, const GatherRecord* recs, const uint32_t* voxels, size_t n) {
     const size_t chunk   = std::min<size_t>(n, 1u << 16);
-    GatherRecord* d_recs = nullptr;
-    uint32_t* d_vox      = nullptr;
-    CK(cudaMalloc(&d_recs, sizeof(GatherRecord) * chunk));
-    CK(cudaMalloc(&d_vox, sizeof(uint32_t) * 3 * kBlockVoxels * chunk));
+    ScopedDev<GatherRecord> recs_buf;
+    ScopedDev<uint32_t> vox_buf; // released on every return path
+    CK(recs_buf.alloc(chunk));
+    CK(vox_buf.alloc((size_t) 3 * kBlockVoxels * chunk));
+    GatherRecord* d_recs = recs_buf.p;
+    uint32_t* d_vox      = vox_buf.p;
     for (size_t first = 0; first < n; first += chunk) {
       const size_t k = std::min(chunk, n - first);
       CK(cudaMemcpyAsync(d_recs, recs + first, sizeof(GatherRecord) * k, cudaMemcpyHostToDevice, m->stream));
@@ -346,7 +361,6 @@ __global__ void __launch_bounds__(128) k_gather_blocks(MapDev m, uint32_t live_c
       m->launches++;
       CK(cudaStreamSynchronize(m->stream));
     }
-    cudaFree(d_recs), cudaFree(d_vox);
     return 0;
   }
 
